@@ -1,0 +1,699 @@
+// rr_plan.cpp — see rr_plan.h.
+#include "rr_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace rr {
+
+namespace {
+
+// SURVEY.md 8(d) contract weights (FP64-pipe thread-instructions per node)
+const double kW[RR_OP_COUNT] = {0, 0, 0, 1, 1, 1, 10, 16, 16, 28, 18, 10, 1, 90, 1, 1, 1, 1, 1, 1};
+
+int arity(uint32_t op)  // == get_arity, /root/reference/rils_rols_cpp/node.h:40-56
+{
+    switch (op) {
+    case RR_OP_CONST:
+    case RR_OP_VAR:
+        return 0;
+    case RR_OP_SIN:
+    case RR_OP_COS:
+    case RR_OP_LN:
+    case RR_OP_EXP:
+    case RR_OP_SQRT:
+    case RR_OP_SQR:
+        return 1;
+    default:
+        return 2;
+    }
+}
+
+uint32_t bin_ins(uint32_t op)
+{
+    switch (op) {
+    case RR_OP_PLUS: return RI_ADD;
+    case RR_OP_MINUS: return RI_SUB;
+    case RR_OP_MULTIPLY: return RI_MUL;
+    case RR_OP_DIVIDE: return RI_DIV;
+    case RR_OP_POW: return RI_POW;
+    case RR_OP_LESS_THAN: return RI_LT;
+    case RR_OP_GREATER_THAN: return RI_GT;
+    case RR_OP_EQUAL: return RI_EQ;
+    case RR_OP_NOT_EQUAL: return RI_NE;
+    case RR_OP_MIN: return RI_MIN;
+    case RR_OP_MAX: return RI_MAX;
+    }
+    return RI_END;
+}
+
+uint32_t un_ins(uint32_t op)
+{
+    switch (op) {
+    case RR_OP_SIN: return RI_SIN;
+    case RR_OP_COS: return RI_COS;
+    case RR_OP_LN: return RI_LN;
+    case RR_OP_EXP: return RI_EXP;
+    case RR_OP_SQRT: return RI_SQRT;
+    case RR_OP_SQR: return RI_SQR;
+    }
+    return RI_END;
+}
+
+constexpr uint32_t STAGED = 0x8000u;  // pre-patch marker: operand is a staged column, not a slot
+
+}  // namespace
+
+BatchPlanner::BatchPlanner(const rr_batch *b, int32_t d) : b_(b), d_(d) {}
+
+std::string BatchPlanner::build_term(int32_t code_begin, int32_t code_len, Term &t) const
+{
+    t.code_begin = code_begin;
+    t.code_len = code_len;
+    t.nodes.clear();
+    t.nodes.reserve(code_len);
+    t.w = 0.0;
+    std::vector<int32_t> st;
+    for (int32_t i = 0; i < code_len; ++i) {
+        const uint32_t w = b_->code[code_begin + i];
+        const uint32_t op = RR_INS_OP(w), arg = RR_INS_ARG(w);
+        if (op == RR_OP_NONE || op >= RR_OP_COUNT) return "bad opcode";
+        TermNode n;
+        n.op = (uint8_t)op;
+        const int ar = arity(op);
+        if ((int)st.size() < ar) return "malformed postfix (stack underflow)";
+        if (op == RR_OP_CONST) {
+            if ((int32_t)arg >= b_->n_consts) return "constant index out of range";
+            n.cval = b_->consts[arg];
+        } else if (op == RR_OP_VAR) {
+            if ((int32_t)arg >= d_) return "feature index out of range";
+            n.var = (int32_t)arg;
+        } else {
+            if (ar == 2) { n.right = st.back(); st.pop_back(); }
+            n.left = st.back();
+            st.pop_back();
+            const TermNode &L = t.nodes[n.left];
+            if (ar == 1) {
+                n.need = L.need;
+            } else {
+                const TermNode &R = t.nodes[n.right];
+                if (R.leaf()) n.need = L.need;
+                else if (L.leaf()) n.need = R.need;
+                else n.need = L.need == R.need ? L.need + 1 : std::max(L.need, R.need);
+            }
+        }
+        t.w += kW[op];
+        st.push_back((int32_t)t.nodes.size());
+        t.nodes.push_back(n);
+    }
+    if (st.size() != 1) return "postfix does not reduce to one tree";
+    t.is_const_one = code_len == 1 && t.nodes[0].op == RR_OP_CONST && t.nodes[0].cval == 1.0;
+    return "";
+}
+
+std::string BatchPlanner::analyse(bool no_cse)
+{
+    if (!b_ || b_->n_cand < 0) return "null batch";
+    if (b_->n_cand == 0) return "";
+    if (!b_->cand_term_begin || !b_->term_code_begin || !b_->code) return "null batch arrays";
+    const int32_t n_terms = b_->cand_term_begin[b_->n_cand];
+    if (b_->cand_term_begin[0] != 0 || b_->term_code_begin[0] != 0) return "offset arrays must start at 0";
+    term_id_.assign(n_terms, -1);
+    terms_.clear();
+    std::unordered_map<std::string, int32_t> seen;
+    std::string key;
+    for (int32_t t = 0; t < n_terms; ++t) {
+        const int32_t c0 = b_->term_code_begin[t], c1 = b_->term_code_begin[t + 1];
+        if (c1 <= c0) return "empty term program";
+        key.clear();
+        for (int32_t i = c0; i < c1; ++i) {
+            const uint32_t w = b_->code[i];
+            const uint32_t op = RR_INS_OP(w);
+            key.push_back((char)op);
+            if (op == RR_OP_CONST) {
+                const uint32_t a = RR_INS_ARG(w);
+                if ((int32_t)a >= b_->n_consts) return "constant index out of range";
+                char buf[8];
+                std::memcpy(buf, &b_->consts[a], 8);
+                key.append(buf, 8);
+            } else if (op == RR_OP_VAR) {
+                const uint32_t a = RR_INS_ARG(w);
+                key.append((const char *)&a, 4);
+            }
+        }
+        if (!no_cse) {
+            auto it = seen.find(key);
+            if (it != seen.end()) { term_id_[t] = it->second; continue; }
+        }
+        Term tm;
+        std::string err = build_term(c0, c1 - c0, tm);
+        if (!err.empty()) return err;
+        const int32_t id = (int32_t)terms_.size();
+        terms_.push_back(std::move(tm));
+        term_id_[t] = id;
+        if (!no_cse) seen.emplace(key, id);
+    }
+    // contract weights, SURVEY.md 8(d): W(c) = sum w(op) + k(k+1)/2 + k + (k + 2)
+    cand_w_.assign(b_->n_cand, 0.0);
+    w_contract_ = 0.0;
+    max_k_ = 0;
+    for (int32_t c = 0; c < b_->n_cand; ++c) {
+        const int32_t t0 = b_->cand_term_begin[c], t1 = b_->cand_term_begin[c + 1];
+        if (t1 < t0) return "cand_term_begin not monotone";
+        if (b_->mode == RR_MODE_EVAL_ONLY && t1 - t0 != 1) return "EVAL_ONLY needs exactly one program per candidate";
+        double w = 0.0;
+        for (int32_t t = t0; t < t1; ++t) w += terms_[term_id_[t]].w;
+        if (b_->mode == RR_MODE_OLS_FIT) {
+            const double k = t1 - t0 + 1;
+            w += k * (k + 1) / 2 + k + k + 2;
+            max_k_ = std::max(max_k_, (int32_t)k);
+        } else {
+            w += 2;
+        }
+        cand_w_[c] = w;
+        w_contract_ += w;
+    }
+    return "";
+}
+
+// ---------------------------------------------------------------------------------------------
+// chunk builder
+// ---------------------------------------------------------------------------------------------
+struct BatchPlanner::Chunk {
+    const BatchPlanner &bp;
+    SweepPlan &P;
+    const PlanLimits &lim;
+    int32_t pc_begin, dot_base, col_begin;
+    std::unordered_map<int32_t, int32_t> colmap;  // global column -> staged index
+    int32_t pool_cap = 0;                          // slots available in this chunk
+    std::vector<int32_t> slot_term;                // slot -> cached term (-1 free, -2 temp)
+    std::vector<uint64_t> slot_stamp;
+    std::vector<uint64_t> slot_pin;
+    std::unordered_map<int32_t, int32_t> term_slot;
+    uint64_t clock = 1, epoch = 1;
+    std::string err;
+
+    Chunk(const BatchPlanner &bp_, SweepPlan &P_, const PlanLimits &lim_, const std::vector<int32_t> &cols)
+        : bp(bp_), P(P_), lim(lim_)
+    {
+        pc_begin = (int32_t)P.ins.size();
+        dot_base = P.n_dots;
+        col_begin = (int32_t)P.cols.size();
+        for (int32_t g : cols) {
+            colmap.emplace(g, (int32_t)colmap.size());
+            P.cols.push_back(g);
+        }
+        pool_cap = lim.tile_cols - (int32_t)cols.size();
+    }
+
+    uint32_t staged(int32_t gcol)
+    {
+        auto it = colmap.find(gcol);
+        if (it == colmap.end()) { err = "internal: column not staged"; return STAGED; }
+        return STAGED | (uint32_t)it->second;
+    }
+
+    void emit(uint32_t w0, uint32_t w1, double imm, double w)
+    {
+        RRIns i;
+        i.w0 = w0;
+        i.w1 = w1;
+        i.imm = imm;
+        P.ins.push_back(i);
+        P.w_issued += w;
+    }
+
+    // a free slot, growing the pool or evicting the least recently used unpinned cached term
+    int32_t alloc_slot(int32_t owner)
+    {
+        int32_t s = -1;
+        for (size_t i = 0; i < slot_term.size(); ++i)
+            if (slot_term[i] == -1) { s = (int32_t)i; break; }
+        if (s < 0 && (int32_t)slot_term.size() < pool_cap) {
+            s = (int32_t)slot_term.size();
+            slot_term.push_back(-1);
+            slot_stamp.push_back(0);
+            slot_pin.push_back(0);
+        }
+        if (s < 0) {
+            uint64_t best = ~0ull;
+            for (size_t i = 0; i < slot_term.size(); ++i)
+                if (slot_term[i] >= 0 && slot_pin[i] != epoch && slot_stamp[i] < best) {
+                    best = slot_stamp[i];
+                    s = (int32_t)i;
+                }
+            if (s < 0) { err = "tile slots exhausted"; return 0; }
+            term_slot.erase(slot_term[s]);
+        }
+        slot_term[s] = owner;
+        slot_stamp[s] = clock++;
+        slot_pin[s] = epoch;
+        if (owner >= 0) term_slot[owner] = s;
+        return s;
+    }
+    void free_slot(int32_t s)
+    {
+        if (slot_term[s] >= 0) term_slot.erase(slot_term[s]);
+        slot_term[s] = -1;
+    }
+    int32_t lookup(int32_t term)
+    {
+        auto it = term_slot.find(term);
+        if (it == term_slot.end()) return -1;
+        slot_stamp[it->second] = clock++;
+        slot_pin[it->second] = epoch;
+        return it->second;
+    }
+    void unpin_all() { ++epoch; }
+
+    // leaves t = value(node x)
+    void gen(const Term &T, int32_t x)
+    {
+        const TermNode &n = T.nodes[x];
+        if (n.op == RR_OP_CONST) { emit(RI_LOAD | RF_CONST, 0, n.cval, 0); return; }
+        if (n.op == RR_OP_VAR) { emit(RI_LOAD, staged(n.var), 0.0, 0); return; }
+        const int ar = arity(n.op);
+        if (ar == 1) {
+            gen(T, n.left);
+            emit(un_ins(n.op), 0, 0.0, kW[n.op]);
+            return;
+        }
+        const TermNode &L = T.nodes[n.left], &R = T.nodes[n.right];
+        const uint32_t op = bin_ins(n.op);
+        auto leaf_operand = [&](const TermNode &lf, uint32_t extra) {
+            if (lf.op == RR_OP_CONST) emit(op | RF_CONST | extra, 0, lf.cval, kW[n.op]);
+            else emit(op | extra, staged(lf.var), 0.0, kW[n.op]);
+        };
+        if (R.leaf()) {
+            gen(T, n.left);
+            leaf_operand(R, 0);
+        } else if (L.leaf()) {
+            gen(T, n.right);
+            leaf_operand(L, RF_SWAP);
+        } else if (L.need >= R.need) {
+            gen(T, n.left);
+            const int32_t s = alloc_slot(-2);
+            emit(RI_ST, (uint32_t)s, 0.0, 0);
+            gen(T, n.right);
+            emit(op | RF_SWAP, (uint32_t)s, 0.0, kW[n.op]);  // t = L(slot) op R(t)
+            free_slot(s);
+        } else {
+            gen(T, n.right);
+            const int32_t s = alloc_slot(-2);
+            emit(RI_ST, (uint32_t)s, 0.0, 0);
+            gen(T, n.left);
+            emit(op, (uint32_t)s, 0.0, kW[n.op]);  // t = L(t) op R(slot)
+            free_slot(s);
+        }
+    }
+
+    void gen_term(int32_t u)
+    {
+        const Term &T = bp.term(u);
+        gen(T, (int32_t)T.nodes.size() - 1);
+        P.n_term_evals++;
+    }
+
+    // make term u resident in a slot; returns slot, sets tos = true when t holds its value
+    int32_t ensure(int32_t u, bool &tos)
+    {
+        int32_t s = lookup(u);
+        if (s >= 0) { tos = false; return s; }
+        gen_term(u);
+        s = alloc_slot(u);
+        emit(RI_ST, (uint32_t)s, 0.0, 0);
+        tos = true;
+        return s;
+    }
+
+    int32_t dot(uint32_t op, uint32_t ka, uint32_t a, uint32_t kb, uint32_t b)
+    {
+        emit(RR_DOT_W0(op, ka, kb), (a & 0xffffu) | ((b & 0xffffu) << 16), 0.0, op == RI_DOTDD ? 10.0 : 1.0);
+        const int32_t id = P.n_dots;
+        P.n_dots += op == RI_DOTDD ? 2 : (op == RI_CLSMET ? 3 : 1);
+        P.n_dot_ins++;
+        return id;
+    }
+
+    void close()
+    {
+        emit(RI_END, 0, 0.0, 0);
+        const int32_t n_cols = (int32_t)colmap.size();
+        auto patch = [&](uint32_t v) -> uint32_t { return (v & STAGED) ? (v & 0x7fffu) : (uint32_t)n_cols + v; };
+        for (size_t i = pc_begin; i < P.ins.size(); ++i) {
+            RRIns &x = P.ins[i];
+            const uint32_t op = x.w0 & 0xffu;
+            if (op == RI_DOT || op == RI_DOTDD || op == RI_CLSMET) {
+                uint32_t a = x.w1 & 0xffffu, b = x.w1 >> 16;
+                if (RR_DOT_KA(x.w0) == RD_COL) a = patch(a);
+                if (RR_DOT_KB(x.w0) == RD_COL) b = patch(b);
+                x.w1 = a | (b << 16);
+            } else if (op == RI_ST || op == RI_AXPY || (op >= RI_LOAD && op <= RI_MAX && op != RI_STG && !(x.w0 & RF_CONST))) {
+                x.w1 = patch(x.w1);
+            }
+        }
+        RRChunk c;
+        std::memset(&c, 0, sizeof(c));
+        c.pc_begin = pc_begin;
+        c.dot_base = dot_base;
+        c.n_dots = P.n_dots - dot_base;
+        c.col_begin = col_begin;
+        c.n_cols = n_cols;
+        P.chunks.push_back(c);
+        P.max_tile_cols = std::max(P.max_tile_cols, n_cols + (int32_t)slot_term.size());
+    }
+};
+
+namespace {
+
+struct Unit {
+    std::vector<int32_t> terms;  // distinct term ids this unit touches
+    double w;
+};
+
+// cut the unit list into chunks: by contract weight (target_chunks) and by tile capacity
+struct ChunkSpec {
+    int32_t begin, end;
+    std::vector<int32_t> cols;
+};
+
+void term_vars(const Term &t, std::vector<int32_t> &out)
+{
+    for (const TermNode &n : t.nodes)
+        if (n.op == RR_OP_VAR) out.push_back(n.var);
+}
+
+}  // namespace
+
+static std::string cut_chunks(const BatchPlanner &bp, const std::vector<Unit> &units, const PlanLimits &lim,
+                              const std::vector<int32_t> &always_cols, int32_t min_slots,
+                              std::vector<ChunkSpec> &out)
+{
+    double total = 0.0;
+    for (const Unit &u : units) total += u.w;
+    const double target = lim.target_chunks > 1 ? total / lim.target_chunks : 1e300;
+    const int32_t cap_cols = lim.tile_cols - min_slots;
+    if (cap_cols < (int32_t)always_cols.size() + 1) return "tile too small for the required slots";
+    size_t i = 0;
+    std::vector<int32_t> vars;
+    while (i < units.size()) {
+        ChunkSpec cs;
+        cs.begin = (int32_t)i;
+        std::vector<int32_t> cols(always_cols);
+        std::vector<char> have;
+        auto has = [&](int32_t v) { return v < (int32_t)have.size() && have[v]; };
+        auto add = [&](int32_t v) {
+            if (v >= (int32_t)have.size()) have.resize(v + 1, 0);
+            have[v] = 1;
+            cols.push_back(v);
+        };
+        for (int32_t v : always_cols) {
+            if (v >= (int32_t)have.size()) have.resize(v + 1, 0);
+            have[v] = 1;
+        }
+        double w = 0.0;
+        while (i < units.size()) {
+            vars.clear();
+            for (int32_t t : units[i].terms) term_vars(bp.term(t), vars);
+            std::sort(vars.begin(), vars.end());
+            vars.erase(std::unique(vars.begin(), vars.end()), vars.end());
+            int32_t fresh = 0;
+            for (int32_t v : vars)
+                if (!has(v)) ++fresh;
+            if ((int32_t)cols.size() + fresh > cap_cols) {
+                if ((int32_t)i == cs.begin) return "a candidate uses more feature columns than the tile can stage";
+                break;
+            }
+            for (int32_t v : vars)
+                if (!has(v)) add(v);
+            w += units[i].w;
+            ++i;
+            if (w >= target) break;
+        }
+        cs.end = (int32_t)i;
+        cs.cols = std::move(cols);
+        out.push_back(std::move(cs));
+    }
+    return "";
+}
+
+static int32_t max_need(const BatchPlanner &bp, const std::vector<Unit> &units)
+{
+    int32_t m = 0;
+    for (const Unit &u : units)
+        for (int32_t t : u.terms) m = std::max(m, bp.term(t).nodes.back().need);
+    return m;
+}
+
+std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> *subset,
+                                    bool dd, SweepPlan &P, std::vector<int32_t> &cand_dot,
+                                    std::vector<int32_t> &cand_dot_begin)
+{
+    std::vector<int32_t> list;
+    if (subset) list = *subset;
+    else {
+        list.resize(b_->n_cand);
+        for (int32_t c = 0; c < b_->n_cand; ++c) list[c] = c;
+    }
+    std::vector<Unit> units(list.size());
+    for (size_t i = 0; i < list.size(); ++i) {
+        const int32_t c = list[i];
+        for (int32_t t = b_->cand_term_begin[c]; t < b_->cand_term_begin[c + 1]; ++t)
+            units[i].terms.push_back(term_id_[t]);
+        units[i].w = cand_w_[c];
+    }
+    const int32_t need = max_need(*this, units);
+    // slots wanted: all terms of the widest candidate resident + spill temporaries; if the tile
+    // cannot give that, pairs are scheduled in blocks (see below)
+    const int32_t min_slots = std::min(std::max(4, need + 3), std::max(4, lim.tile_cols / 2));
+    std::vector<ChunkSpec> specs;
+    std::string err = cut_chunks(*this, units, lim, {cols.yc}, min_slots, specs);
+    if (!err.empty()) return err;
+
+    const uint32_t DOP = dd ? RI_DOTDD : RI_DOT;
+    cand_dot.clear();
+    cand_dot_begin.assign(1, 0);
+    // dot key -> id, global over the plan (a dot computed in an earlier chunk is simply reused)
+    std::unordered_map<uint64_t, int32_t> dots;
+    const int64_t KEY_YC = -1, KEY_ONE = -2;
+    auto key = [](int64_t a, int64_t b) -> uint64_t {
+        if (a > b) std::swap(a, b);
+        return ((uint64_t)(uint32_t)(int32_t)a << 32) | (uint64_t)(uint32_t)(int32_t)b;
+    };
+    for (const ChunkSpec &cs : specs) {
+        Chunk ch(*this, P, lim, cs.cols);
+        const uint32_t yc_col = ch.staged(cols.yc);
+        for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
+            const std::vector<int32_t> &T = units[ui].terms;
+            const int32_t m = (int32_t)T.size();
+            // which distinct terms take part in a dot that is still missing
+            std::vector<int32_t> N;
+            auto missing = [&](int64_t a, int64_t b) { return dots.find(key(a, b)) == dots.end(); };
+            for (int32_t i = 0; i < m; ++i) {
+                bool miss = missing(T[i], KEY_YC) || missing(T[i], KEY_ONE);
+                for (int32_t j = 0; j < m && !miss; ++j) miss = missing(T[i], T[j]);
+                if (miss && std::find(N.begin(), N.end(), T[i]) == N.end()) N.push_back(T[i]);
+            }
+            ch.unpin_all();
+            const int32_t tmp_need = need + 1;
+            const int32_t room = ch.pool_cap - tmp_need;
+            if (room < 2) return "tile too small";
+            auto pair_dots = [&](int32_t u, bool tos, int32_t su, const std::vector<int32_t> &done) {
+                // dots of u with itself, yc, ones and every already-resident partner
+                const uint32_t ka = tos ? RD_TOS : RD_COL;
+                if (missing(u, u)) dots[key(u, u)] = ch.dot(DOP, ka, su, ka, su);
+                if (missing(u, KEY_YC)) dots[key(u, KEY_YC)] = ch.dot(DOP, ka, su, RD_COL, yc_col);
+                if (missing(u, KEY_ONE)) dots[key(u, KEY_ONE)] = ch.dot(DOP, ka, su, RD_ONE, 0);
+                for (int32_t v : done) {
+                    if (v == u || !missing(u, v)) continue;
+                    // only pairs that some candidate of this unit needs
+                    const int32_t sv = ch.lookup(v);
+                    if (sv < 0) { ch.err = "internal: partner not resident"; return; }
+                    dots[key(u, v)] = ch.dot(DOP, ka, su, RD_COL, (uint32_t)sv);
+                }
+            };
+            if ((int32_t)N.size() <= room) {
+                // a missing pair has both ends in N (missing() is symmetric), so processing N in
+                // order emits each pair once, when its later term becomes resident
+                std::vector<int32_t> done;
+                for (int32_t u : N) {
+                    bool tos = false;
+                    const int32_t su = ch.ensure(u, tos);
+                    pair_dots(u, tos, su, done);
+                    done.push_back(u);
+                    if (!ch.err.empty()) return ch.err;
+                }
+            } else {
+                // blocked schedule: groups of g terms; for every pair of groups make both resident
+                const int32_t g = std::max(1, room / 2);
+                const int32_t ng = ((int32_t)N.size() + g - 1) / g;
+                for (int32_t ga = 0; ga < ng; ++ga)
+                    for (int32_t gb = ga; gb < ng; ++gb) {
+                        ch.unpin_all();
+                        std::vector<int32_t> done;
+                        for (int32_t grp : {ga, gb}) {
+                            for (int32_t i = grp * g; i < std::min((grp + 1) * g, (int32_t)N.size()); ++i) {
+                                const int32_t u = N[i];
+                                if (std::find(done.begin(), done.end(), u) != done.end()) continue;
+                                bool tos = false;
+                                const int32_t su = ch.ensure(u, tos);
+                                pair_dots(u, tos, su, done);
+                                done.push_back(u);
+                                if (!ch.err.empty()) return ch.err;
+                            }
+                            if (ga == gb) break;
+                        }
+                    }
+            }
+            // index table of this candidate
+            for (int32_t i = 0; i < m; ++i)
+                for (int32_t j = i; j < m; ++j) {
+                    auto it = dots.find(key(T[i], T[j]));
+                    if (it == dots.end()) return "internal: missing Gram dot";
+                    cand_dot.push_back(it->second);
+                }
+            for (int32_t i = 0; i < m; ++i) cand_dot.push_back(dots[key(T[i], KEY_YC)]);
+            for (int32_t i = 0; i < m; ++i) cand_dot.push_back(dots[key(T[i], KEY_ONE)]);
+            cand_dot_begin.push_back((int32_t)cand_dot.size());
+        }
+        if (!ch.err.empty()) return ch.err;
+        ch.close();
+    }
+    return "";
+}
+
+std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> &subset,
+                                        const double *coef, SweepPlan &P, std::vector<int32_t> &cand_dot,
+                                        std::vector<int32_t> &cand_dot_begin)
+{
+    std::vector<Unit> units(subset.size());
+    for (size_t i = 0; i < subset.size(); ++i) {
+        const int32_t c = subset[i];
+        for (int32_t t = b_->cand_term_begin[c]; t < b_->cand_term_begin[c + 1]; ++t)
+            units[i].terms.push_back(term_id_[t]);
+        units[i].w = cand_w_[c];
+    }
+    const int32_t need = max_need(*this, units);
+    int32_t widest = 0;
+    for (const Unit &u : units) widest = std::max(widest, (int32_t)u.terms.size());
+    const int32_t min_slots = widest + need + 2;
+    std::vector<ChunkSpec> specs;
+    std::string err = cut_chunks(*this, units, lim, {cols.y}, min_slots, specs);
+    if (!err.empty()) return err + " (residual pass)";
+    cand_dot.clear();
+    cand_dot_begin.assign(1, 0);
+    for (const ChunkSpec &cs : specs) {
+        Chunk ch(*this, P, lim, cs.cols);
+        const uint32_t y_col = ch.staged(cols.y);
+        for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
+            const int32_t c = subset[ui];
+            const std::vector<int32_t> &T = units[ui].terms;
+            const int32_t m = (int32_t)T.size();
+            const double *cf = coef + b_->cand_term_begin[c] + c;
+            ch.unpin_all();
+            std::vector<int32_t> slot(m);
+            for (int32_t i = 0; i < m; ++i) {
+                bool tos;
+                slot[i] = ch.ensure(T[i], tos);
+                if (!ch.err.empty()) return ch.err;
+            }
+            // yhat in the association order of rils_rols_cpp.cpp:488-515
+            bool first = true;
+            for (int32_t i = 0; i < m; ++i) {
+                const double ci = cf[i];
+                if (ci == 0.0) continue;  // snapped away (value_zero)
+                if (first) {
+                    ch.emit(RI_LOAD, (uint32_t)slot[i], 0.0, 0);
+                    if (ci != 1.0) ch.emit(RI_MUL | RF_CONST | RF_SWAP, 0, ci, 1);
+                    first = false;
+                } else if (ci == 1.0) {
+                    ch.emit(RI_ADD, (uint32_t)slot[i], 0.0, 1);
+                } else {
+                    ch.emit(RI_AXPY, (uint32_t)slot[i], ci, 2);
+                }
+            }
+            if (cf[m] != 0.0) {
+                if (first) ch.emit(RI_LOAD | RF_CONST, 0, cf[m], 0);
+                else ch.emit(RI_ADD | RF_CONST, 0, cf[m], 1);
+                first = false;
+            }
+            if (first) ch.emit(RI_LOAD | RF_CONST, 0, 0.0, 0);
+            ch.emit(RI_SUB | RF_SWAP, y_col, 0.0, 1);  // t = y - yhat
+            cand_dot.push_back(ch.dot(RI_DOT, RD_TOS, 0, RD_TOS, 0));
+            for (int32_t i = 0; i < m; ++i) cand_dot.push_back(ch.dot(RI_DOT, RD_TOS, 0, RD_COL, (uint32_t)slot[i]));
+            cand_dot.push_back(ch.dot(RI_DOT, RD_TOS, 0, RD_ONE, 0));
+            cand_dot_begin.push_back((int32_t)cand_dot.size());
+        }
+        if (!ch.err.empty()) return ch.err;
+        ch.close();
+    }
+    return "";
+}
+
+std::string BatchPlanner::plan_eval(const PlanLimits &lim, const ColIds &cols, bool metrics, SweepPlan &P,
+                                    std::vector<int32_t> &cand_dot)
+{
+    std::vector<Unit> units(b_->n_cand);
+    for (int32_t c = 0; c < b_->n_cand; ++c) {
+        units[c].terms.push_back(term_id_[b_->cand_term_begin[c]]);
+        units[c].w = cand_w_[c];
+    }
+    const int32_t need = max_need(*this, units);
+    std::vector<ChunkSpec> specs;
+    std::string err = cut_chunks(*this, units, lim, {cols.y}, need + 2, specs);
+    if (!err.empty()) return err;
+    cand_dot.assign(b_->n_cand, DOT_NONE);
+    std::unordered_map<int32_t, int32_t> done;  // identical programs share their result
+    for (const ChunkSpec &cs : specs) {
+        Chunk ch(*this, P, lim, cs.cols);
+        const uint32_t y_col = ch.staged(cols.y);
+        for (int32_t c = cs.begin; c < cs.end; ++c) {
+            const int32_t u = units[c].terms[0];
+            auto it = done.find(u);
+            if (it != done.end()) { cand_dot[c] = it->second; continue; }
+            ch.unpin_all();
+            ch.gen_term(u);
+            int32_t id;
+            if (metrics) {
+                id = ch.dot(RI_CLSMET, RD_TOS, 0, RD_COL, y_col);
+            } else {
+                ch.emit(RI_SUB | RF_SWAP, y_col, 0.0, 1);  // t = y - yhat
+                id = ch.dot(RI_DOT, RD_TOS, 0, RD_TOS, 0);
+            }
+            done.emplace(u, id);
+            cand_dot[c] = id;
+            if (!ch.err.empty()) return ch.err;
+        }
+        ch.close();
+    }
+    return "";
+}
+
+std::string BatchPlanner::plan_materialise(const PlanLimits &lim, const ColIds &cols, SweepPlan &P)
+{
+    (void)cols;
+    std::vector<Unit> units(terms_.size());
+    for (size_t u = 0; u < terms_.size(); ++u) {
+        units[u].terms.push_back((int32_t)u);
+        units[u].w = terms_[u].w + 1;
+    }
+    const int32_t need = max_need(*this, units);
+    std::vector<ChunkSpec> specs;
+    std::string err = cut_chunks(*this, units, lim, {}, need + 2, specs);
+    if (!err.empty()) return err;
+    for (const ChunkSpec &cs : specs) {
+        Chunk ch(*this, P, lim, cs.cols);
+        for (int32_t u = cs.begin; u < cs.end; ++u) {
+            ch.unpin_all();
+            ch.gen_term(u);
+            ch.emit(RI_STG, (uint32_t)u, 0.0, 0);
+            if (!ch.err.empty()) return ch.err;
+        }
+        ch.close();
+    }
+    P.n_stg_cols = (int32_t)terms_.size();
+    return "";
+}
+
+}  // namespace rr

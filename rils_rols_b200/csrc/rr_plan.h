@@ -1,0 +1,118 @@
+// rr_plan.h — host-side planner: rr_batch (postfix trees) -> sweep programs.
+//
+// This is the "tree -> compact bytecode batch" compiler of the north star plus the
+// cross-candidate sharing SURVEY.md App. B.9 measures (only ~10 % of the term instances
+// of a local-search neighbourhood are distinct): terms are hashed, evaluated once per
+// sample and kept in tile slots; Gram / A^T y entries are keyed by the (term, term) pair
+// and reduced once.
+#ifndef RR_PLAN_H
+#define RR_PLAN_H
+
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rr_b200.h"
+#include "rr_isa.h"
+
+namespace rr {
+
+// global column ids of the engine's sample-major matrix: features 0..d-1, then
+struct ColIds {
+    int y;   // d     : y
+    int yc;  // d + 1 : y - mean(y)
+};
+
+struct TermNode {
+    uint8_t op;
+    int32_t left = -1, right = -1;  // node indices
+    int32_t var = -1;
+    double cval = 0.0;
+    int32_t need = 0;  // Sethi-Ullman spill need
+    bool leaf() const { return op == RR_OP_CONST || op == RR_OP_VAR; }
+};
+
+struct Term {
+    int32_t code_begin = 0, code_len = 0;  // first instance in the batch code
+    std::vector<TermNode> nodes;           // postfix order, root = back()
+    double w = 0.0;                        // SURVEY 8(d) contract weight of one evaluation
+    bool is_const_one = false;
+};
+
+struct SweepPlan {
+    std::vector<RRIns> ins;
+    std::vector<RRChunk> chunks;
+    std::vector<int32_t> cols;  // staged global column ids, per chunk [col_begin, col_begin+n_cols)
+    int32_t n_dots = 0;
+    int32_t max_tile_cols = 0;  // max over chunks of staged columns + slots used
+    int32_t n_stg_cols = 0;     // columns written by RI_STG
+    double w_issued = 0.0;      // contract-weighted FP64 work actually issued, per sample
+    uint64_t n_term_evals = 0;
+    uint64_t n_dot_ins = 0;
+    bool empty() const { return chunks.empty(); }
+};
+
+struct PlanLimits {
+    int32_t tile_cols = 56;  // columns that fit the shared-memory tile for the chosen tile height
+    int32_t tmp_slots = 8;   // spill temporaries reserved per chunk
+    int32_t target_chunks = 1;
+    bool no_cse = false;
+};
+
+// dot-id sentinels used in the per-candidate index tables
+enum : int32_t { DOT_NONE = -1 };
+
+class BatchPlanner {
+public:
+    BatchPlanner(const rr_batch *b, int32_t d);
+    // returns "" or an error description (malformed batch)
+    std::string analyse(bool no_cse);
+
+    int32_t n_cand() const { return b_->n_cand; }
+    int32_t n_terms_distinct() const { return (int32_t)terms_.size(); }
+    int32_t n_term_instances() const { return (int32_t)term_id_.size(); }
+    int32_t k_of(int32_t c) const { return b_->cand_term_begin[c + 1] - b_->cand_term_begin[c] + 1; }
+    int32_t max_k() const { return max_k_; }
+    const std::vector<int32_t> &term_ids() const { return term_id_; }  // per term instance -> distinct id
+    const Term &term(int32_t u) const { return terms_[u]; }
+    double w_contract() const { return w_contract_; }
+    const std::vector<double> &cand_contract_w() const { return cand_w_; }
+
+    // OLS_FIT, Gram path: Gram + A^T yc + column sums for the candidates in `subset`
+    // (nullptr = all). cand_dot: per listed candidate m(m+1)/2 (upper triangle, row-major)
+    // + m (with yc) + m (with ones) dot ids; cand_dot_begin has subset size + 1 entries.
+    // dd = accumulate in double-double (each id then addresses a (hi,lo) pair: id, id+1).
+    std::string plan_gram(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> *subset,
+                          bool dd, SweepPlan &out, std::vector<int32_t> &cand_dot,
+                          std::vector<int32_t> &cand_dot_begin);
+
+    // explicit residual of the model sum_i cs_i t_i + cs_free (snapped coefficients, reference
+    // association order) for the listed candidates: per candidate 1 (r.r) + m (r.t_i) + 1 (r.1) ids.
+    std::string plan_residual(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> &subset,
+                              const double *coef_snapped, SweepPlan &out, std::vector<int32_t> &cand_dot,
+                              std::vector<int32_t> &cand_dot_begin);
+
+    // EVAL_ONLY: ssr of each program as-is; one dot id per candidate. metrics = also the three
+    // classifier reductions (ids cand_dot[c] + 1..3 are then accuracy count, log-loss sum, abs-loss sum).
+    std::string plan_eval(const PlanLimits &lim, const ColIds &cols, bool metrics, SweepPlan &out,
+                          std::vector<int32_t> &cand_dot);
+
+    // materialise every distinct term as a global column (RI_STG u)
+    std::string plan_materialise(const PlanLimits &lim, const ColIds &cols, SweepPlan &out);
+
+private:
+    struct Chunk;
+    const rr_batch *b_;
+    int32_t d_;
+    int32_t max_k_ = 0;
+    std::vector<Term> terms_;
+    std::vector<int32_t> term_id_;
+    std::vector<double> cand_w_;
+    double w_contract_ = 0.0;
+
+    std::string build_term(int32_t code_begin, int32_t code_len, Term &t) const;
+};
+
+}  // namespace rr
+#endif
