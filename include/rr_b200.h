@@ -31,6 +31,12 @@ extern "C" {
 
 #define RR_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define RR_API __attribute__((visibility("default")))
+#else
+#define RR_API
+#endif
+
 /* opcodes == enum class node_type, rils_rols_cpp/node.h:16-38 */
 enum rr_opcode {
     RR_OP_NONE = 0,
@@ -180,43 +186,44 @@ typedef int (*rr_allreduce_fn)(void *dev_buf, size_t count, void *cuda_stream, v
 /* Replaces the data hand-off of fit(): X is FEATURE-major (d columns of n contiguous
  * doubles, the vector<ArrayXd> layout of rils_rols_cpp.cpp:675-698), y has n doubles.
  * device < 0 selects the current device. Data is copied; nothing is retained. */
-int rr_engine_create(const double *X_feature_major, const double *y, int64_t n, int32_t d,
+RR_API int rr_engine_create(const double *X_feature_major, const double *y, int64_t n, int32_t d,
                      int32_t device, uint32_t flags, rr_engine **out);
 /* Same, from the row-major numpy layout the pybind boundary receives
  * (rils_rols_cpp.cpp:690-696): the transpose runs on the device. */
-int rr_engine_create_rowmajor(const double *X_row_major, const double *y, int64_t n, int32_t d,
+RR_API int rr_engine_create_rowmajor(const double *X_row_major, const double *y, int64_t n, int32_t d,
                               int32_t device, uint32_t flags, rr_engine **out);
-void rr_engine_destroy(rr_engine *e);
+RR_API void rr_engine_destroy(rr_engine *e);
 
-/* Install the all-reduce hook and recompute y_mean / sst over all ranks. */
-int rr_engine_set_allreduce(rr_engine *e, rr_allreduce_fn fn, void *user);
+/* Install the all-reduce hook (this engine holds shard `rank` of `world`) and recompute
+ * y_mean / sst over all ranks. fn == NULL removes it. */
+RR_API int rr_engine_set_allreduce(rr_engine *e, rr_allreduce_fn fn, void *user, int32_t rank, int32_t world);
 
-int rr_engine_get_info(const rr_engine *e, rr_engine_info *info);
-int rr_get_stats(const rr_engine *e, rr_stats *stats);
+RR_API int rr_engine_get_info(const rr_engine *e, rr_engine_info *info);
+RR_API int rr_get_stats(const rr_engine *e, rr_stats *stats);
 
 /* Score one neighbourhood. Synchronous: results are valid on return. */
-int rr_score_batch(rr_engine *e, const rr_batch *batch, rr_result *result);
+RR_API int rr_score_batch(rr_engine *e, const rr_batch *batch, rr_result *result);
 
 /* Classifier metrics of rils_rols_cpp.cpp:51-86 for EVAL_ONLY programs (not used by
  * the search, :527): out arrays [n_cand], any may be NULL. */
-int rr_classifier_metrics(rr_engine *e, const rr_batch *batch, double *accuracy, double *log_loss,
+RR_API int rr_classifier_metrics(rr_engine *e, const rr_batch *batch, double *accuracy, double *log_loss,
                           double *abs_loss);
 
 /* predict(): evaluate one program over a caller-supplied FEATURE-major matrix
  * (rils_rols_cpp.cpp:730-750 without the 0.5 threshold). out has n doubles. */
-int rr_predict(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts,
+RR_API int rr_predict(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts,
                int32_t n_consts, const double *X_feature_major, int64_t n, int32_t d, double *out);
-int rr_predict_rowmajor(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts,
+RR_API int rr_predict_rowmajor(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts,
                         int32_t n_consts, const double *X_row_major, int64_t n, int32_t d,
                         double *out);
 
 /* Measured FP64-pipe peak (thread-instructions / s) of the engine's device from a
  * DFMA-only microkernel: the roofline denominator of SURVEY 8(d). */
-int rr_measure_fp64_peak(rr_engine *e, double *dfma_per_second);
+RR_API int rr_measure_fp64_peak(rr_engine *e, double *dfma_per_second);
 
 /* Last error text: of the engine, or of the calling thread when e == NULL. */
-const char *rr_last_error(const rr_engine *e);
-int rr_abi_version(void);
+RR_API const char *rr_last_error(const rr_engine *e);
+RR_API int rr_abi_version(void);
 
 #ifdef __cplusplus
 }
