@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — candidate-fit evals/s (trees x samples / s) of the scoring hot path.
+
+Workload (BASELINE.json configs[4], SURVEY.md 8(d) "config 5"): one local-search neighbourhood of
+4096 candidate trees (<= 50 term nodes, committed in tests/golden/cfg5_neighbourhood.npz) scored in
+OLS_FIT mode (terms -> least-squares coefficients -> residual fitness) over n = 2^24 synthetic
+samples x 20 features, sample-sharded over N GPUs (strong scaling: n is fixed, each rank holds n/N
+rows; one all-reduce of the per-candidate partial sums per sweep).
+
+  python bench.py --gpus N --steps K --warmup W          # one rank per GPU under torchrun for N > 1
+  python bench.py --impl reference ...                   # the reference's own CPU path, same metric
+
+A step = rr_score_batch() on the whole neighbourhood. `value` is timed on the device (CUDA events on
+the engine's stream, X resident in HBM), `e2e` is the wall clock of the same C-ABI call made with
+host batch buffers (program upload + result download inside the timed region). Inputs (2.8 GB) are
+far larger than the 126 MB L2, so nothing is served from cache between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rils_rols_b200 import batch as B  # noqa: E402
+from rils_rols_b200 import workloads  # noqa: E402
+
+METRIC = "candidate_fit_evals_per_sec"
+UNIT = "tree-samples/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        if self.samples:
+            return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+
+
+def reference_trees(R, n_cand: int):
+    """The candidate TREES behind the committed batch: all_candidates(tuned_base, local_search=true)
+    of the unmodified reference, filtered to <= 50 term nodes exactly like tests/golden/make_golden.py."""
+    z = np.load(os.path.join(workloads.GOLDEN_DIR, "cfg5_neighbourhood.npz"))
+    Xs, ys = workloads.cfg5_data(256)
+    hs = R.RefHarness(False, 0.001, 50, 12345)
+    hs.set_data(Xs, ys)
+    trees = []
+    for c in hs.all_candidates(z["tuned_code"], z["tuned_consts"], True):
+        if len(trees) == n_cand:
+            break
+        g = hs.score_list([(c[0], c[1])], True)
+        if int(g["term_code_begin"][-1]) <= 50:
+            trees.append((c[0], c[1]))
+    return trees
+
+
+def cpu_baseline_sample(batch: B.Batch, X, y):
+    """Reference CPU path on a bounded sample of the same workload, 1 core (the reference is
+    single-threaded): all 4096 candidates x 8192 samples and 64 candidates x 2^19 samples
+    (cost is linear in n)."""
+    from oracle import pyoracle as O
+
+    R = O.load_ref()
+    parts, evals, secs = [], 0.0, 0.0
+    trees = reference_trees(R, batch.n_cand) if R is not None else None
+    for (cands, rows) in ((batch.n_cand, 8192), (64, 1 << 19)):
+        rows = min(rows, X.shape[0])
+        if R is not None:
+            h = R.RefHarness(False, 0.001, 50, 12345)
+            h.set_data(X[:rows], y[:rows])
+            dt = h.time_list(trees[:cands], True, 1)  # tune_constants + fitness per candidate
+        else:
+            sub = batch if cands == batch.n_cand else batch.subset(range(cands))
+            t0 = time.perf_counter()
+            O.score_batch(O.feature_major(X[:rows]), y[:rows], sub)
+            dt = time.perf_counter() - t0
+        parts.append(f"{cands} candidates x {rows} samples in {dt:.1f}s")
+        evals += cands * rows
+        secs += dt
+    return {"value": evals / secs, "unit": UNIT, "cores": 1, "kind": "reference" if R is not None else "port",
+            "sample": "; ".join(parts) + (" (unmodified reference, oracle/_ref)" if R is not None else " (oracle/rr_oracle.c)")}
+
+
+def run_reference(args):
+    """--impl reference: the unmodified reference (oracle/_ref: tune_constants + fitness per candidate)
+    on all host cores as independent single-threaded replicas; each step is a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as O
+
+    batch = workloads.cfg5_neighbourhood()
+    rows = args.ref_rows
+    X, y = workloads.cfg5_data(max(rows, 1 << 16))
+    X, y = X[:rows], y[:rows]
+    R = O.load_ref()
+    cores = os.cpu_count() or 1
+    if R is not None:
+        kind = "reference"
+        h = R.RefHarness(False, 0.001, 50, 12345)
+        h.set_data(X, y)
+        trees = reference_trees(R, batch.n_cand)
+
+        def step():
+            return h.time_list(trees, True, cores)
+    else:
+        kind = "port"
+        cores = 1
+        Xfm = O.feature_major(X)
+
+        def step():
+            t0 = time.perf_counter()
+            O.score_batch(Xfm, y, batch)
+            return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        step()
+    total = 0.0
+    for _ in range(args.steps):
+        total += step()
+    evals = float(batch.n_cand) * rows * args.steps
+    value = evals / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cfg5: 4096-candidate LS neighbourhood (OLS_FIT) x {rows}-sample slice of the 2^24 x 20 set",
+                   "n_cand": batch.n_cand, "n": rows, "d": 20},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"each step = all {batch.n_cand} candidates x {rows} samples, {cores} replicas of the single-threaded reference"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 24, help="total samples (default: the named workload, 2^24)")
+    ap.add_argument("--ref-rows", type=int, default=16384, help="--impl reference: samples per step")
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from rils_rols_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    batch = workloads.cfg5_neighbourhood()
+    n_total = args.n
+    X, y = workloads.cfg5_data(n_total)
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    Xs, ys = np.ascontiguousarray(X[lo:hi]), np.ascontiguousarray(y[lo:hi])
+
+    t0 = time.perf_counter()
+    eng = Engine(Xs, ys, rowmajor=True, device=local, flags=args.flags)
+    torch.cuda.synchronize(dev)
+    ingest_s = time.perf_counter() - t0
+    if world > 1:
+        eng.set_allreduce_torch()
+    info = eng.info()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    res = B.Result.alloc(batch)
+    for _ in range(args.warmup):
+        eng.score(batch, res)
+    st0 = eng.stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    dev_ms = sweep_ms = 0.0
+    h2d = d2h = 0
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.score(batch, res)
+        st = eng.stats()
+        dev_ms += st["last_batch_ms"]
+        sweep_ms += st["last_sweep_ms"]
+        h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+    barrier()
+    wall_s = time.perf_counter() - w0
+    clocks = sampler.result()
+    st1 = eng.stats()
+
+    times = torch.tensor([dev_ms, wall_s * 1e3, sweep_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, sweep_ms = (float(v) for v in times.tolist())
+
+    if rank == 0:
+        units = float(batch.n_cand) * float(info.n_total) * args.steps
+        value = units / (dev_ms * 1e-3)
+        e2e = units / (wall_ms * 1e-3)
+        peaks, peak_src = load_peaks()
+        fp64_peak = eng.fp64_peak()  # thread-instructions/s of one GPU, DFMA microkernel, measured now
+        w_contract = st1["w_contract"]  # sum over candidates of SURVEY 8(d) W(c)
+        w_shared = st1["w_shared"]      # work actually issued per sample (after CSE, all passes)
+        n_local = float(info.n)
+        sweep_s = sweep_ms * 1e-3 / args.steps
+        achieved = w_shared * n_local / sweep_s
+        hbm_bytes = 8.0 * n_local * (info.d + 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg5: 4096-candidate LS neighbourhood (<= 50 term nodes), OLS_FIT, n=2^24 x d=20, sample-sharded",
+                       "n_cand": batch.n_cand, "n": int(info.n_total), "d": int(info.d), "rows_per_gpu": int(info.n),
+                       "l2": "inputs_exceed_l2 (2.8 GB of X,y per sweep vs 126 MB L2)", "parallelism": f"sample-shard x{world}",
+                       "ingest_s": ingest_s},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": wall_ms / args.steps},
+            "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "fp64", "kernel": "rr_sweep_kernel", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12,
+                "unit": "T fp64-pipe thread-instr/s", "frac": achieved / fp64_peak,
+                "peak_source": "measured live: DFMA-only microkernel on this GPU (rr_measure_fp64_peak)",
+                "traffic": None,
+                "w_contract_per_sample": w_contract, "w_issued_per_sample": w_shared,
+                "contract_rate_frac": (w_contract * n_local / sweep_s) / fp64_peak,
+                "sweep_ms_per_step": sweep_ms / args.steps,
+                "hbm": {"achieved": hbm_bytes / sweep_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": hbm_bytes / sweep_s / 1e9 / peaks["hbm_gbs"], "peak_source": peak_src,
+                        "algorithmic_bytes_per_sweep": hbm_bytes},
+            },
+            "engine": {k: st1[k] for k in ("refined", "exact", "dd", "nonfinite", "distinct_terms", "term_instances",
+                                           "distinct_dots", "dot_instances", "sweep_launches")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(batch, X, y)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -221,6 +221,29 @@ RR_API int rr_predict_rowmajor(rr_engine *e, const uint32_t *code, int32_t code_
  * DFMA-only microkernel: the roofline denominator of SURVEY 8(d). */
 RR_API int rr_measure_fp64_peak(rr_engine *e, double *dfma_per_second);
 
+/* Host-only tooling (no device work): runs the planner on a batch and returns the engine's internal
+ * instruction stream (rils_rols_b200/csrc/rr_isa.h) so that tests can execute it on the CPU and
+ * check the compiler half of the engine without a GPU.
+ *   kind: 0 Gram, 1 Gram in double-double, 2 EVAL_ONLY, 3 EVAL_ONLY + classifier metrics,
+ *         4 materialise distinct terms, 5 residual (coef_snapped = batch coefficient layout).
+ * All arrays are malloc'ed by the call and released by rr_debug_plan_free. */
+typedef struct rr_debug_plan {
+    int64_t n_ins, n_chunks, n_cols, n_tab, n_tab_begin, n_term_ids;
+    void *ins;           /* RRIns[n_ins], 16 bytes each: u32 w0, u32 w1, f64 imm */
+    void *chunks;        /* RRChunk[n_chunks], 8 x i32: pc_begin, n_ins, dot_base, n_dots, col_begin, n_cols, 0, 0 */
+    int32_t *cols;       /* staged global column ids (features 0..d-1, d = y, d+1 = y - mean) */
+    int32_t *tab;        /* per-candidate dot-id table (layout depends on kind) */
+    int32_t *tab_begin;  /* [n_cand + 1] (kinds 0, 1, 5) */
+    int32_t *term_ids;   /* per term instance -> distinct term */
+    int32_t n_dots, max_tile_cols, n_terms_distinct, reserved;
+    double w_issued, w_contract;
+    char error[256];
+} rr_debug_plan;
+RR_API int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kind, int32_t tile_cols,
+                               int32_t max_slots, int32_t target_chunks, int32_t no_cse,
+                               const double *coef_snapped, rr_debug_plan *out);
+RR_API void rr_debug_plan_free(rr_debug_plan *p);
+
 /* Last error text: of the engine, or of the calling thread when e == NULL. */
 RR_API const char *rr_last_error(const rr_engine *e);
 RR_API int rr_abi_version(void);

@@ -92,7 +92,11 @@ int env_int(const char *name, int dflt)
 }
 
 constexpr int64_t kLdAlign = 1024;
-constexpr size_t kSmemBudget = 227 * 1024 - 512;  // dynamic shared memory per block we plan for
+// shared memory per SM usable by blocks: 227 KB per block opt-in limit; the kernel's static part
+// (instruction windows + mbarriers) and the 1 KB the driver reserves per block come off the top
+constexpr size_t kSmemPerBlockMax = 232448;
+constexpr size_t kSmemPerSM = 233472;
+constexpr size_t kSmemReserved = 1024;
 
 __global__ void k_transpose_rowmajor(const double *__restrict__ Xr, int64_t n, int32_t d, double *__restrict__ Xc,
                                      int64_t ld)
@@ -181,7 +185,7 @@ struct rr_engine {
     int64_t n = 0, ld = 0, n_total = 0;
     int32_t d = 0;
     int exact_max_n = 4096;
-    int s_pref = 0;  // 0 = auto
+    int s_pref = 0, th_pref = 0, occ_pref = 0, slots_pref = 0;  // 0 = auto (env RR_B200_S / _TH / _OCC / _SLOTS)
     DevBuf X;        // (d + 2) * ld doubles
     double y_mean = 0, sst = 0, sum_yc = 0;
     rr::SolveConsts sc{};
@@ -228,12 +232,35 @@ struct rr_engine {
 
 namespace {
 
-int tile_cols_for(int S) { return (int)(kSmemBudget / ((size_t)rr::kSweepThreads * S * 8)); }
+// launch shape of the interpreter: S samples per thread, TH threads per block, `occ` blocks per SM
+// planned for (bounds the shared-memory tile and therefore the number of value slots)
+struct SweepCfg {
+    int S, TH, occ;
+    int T() const { return S * TH; }
+    size_t dyn_smem_budget() const
+    {
+        const size_t per_block = std::min(kSmemPerBlockMax, kSmemPerSM / (size_t)occ - kSmemReserved);
+        return per_block - rr::kSweepStaticSmem;
+    }
+    // columns the planner may use; one more is kept for the kernel's scratch column
+    int tile_cols() const { return (int)std::min<size_t>(dyn_smem_budget() / ((size_t)T() * 8), 0x7000) - 1; }
+};
 
-int choose_S(const rr_engine *e)
+SweepCfg choose_cfg(const rr_engine *e)
 {
-    if (e->s_pref == 1 || e->s_pref == 2 || e->s_pref == 4) return e->s_pref;
-    return e->n >= (1 << 16) ? 2 : 1;
+    SweepCfg c;
+    // measured on B200 (profiles/r1_config_sweep.txt): 2 samples per thread in 128-thread blocks,
+    // 3 blocks per SM, is the best trade between per-dispatch overhead (wants more samples per
+    // thread) and latency hiding (wants more warps) under the shared-memory cap on samples in flight
+    const bool big = e->n >= (1 << 15);
+    c.S = e->s_pref ? e->s_pref : (big ? 2 : 1);
+    c.TH = e->th_pref ? e->th_pref : 128;
+    c.occ = e->occ_pref ? e->occ_pref : (c.T() >= 1024 ? 1 : (c.T() >= 512 ? 2 : (c.T() >= 256 ? 3 : 4)));
+    // the tile must stage the feature columns a chunk can touch plus a handful of value slots
+    const int want = std::min(e->d, 24) + 1 + 6;
+    while (c.tile_cols() < want && c.occ > 1) --c.occ;
+    while (c.tile_cols() < want && c.S > 1) c.S /= 2;
+    return c;
 }
 
 template <typename T> int upload(rr_engine *e, DevBuf &buf, const T *src, size_t count)
@@ -245,21 +272,33 @@ template <typename T> int upload(rr_engine *e, DevBuf &buf, const T *src, size_t
     return RR_OK;
 }
 
-using SweepKernel = void (*)(const rr::SweepArgs);
-SweepKernel sweep_kernel_for(int S)
+using SweepKernel = void (*)(const rr::SweepArgs, const int);
+template <bool SP> SweepKernel sweep_kernel_sel(const SweepCfg &c)
 {
-    switch (S) {
-    case 1: return rr::rr_sweep_kernel<1>;
-    case 2: return rr::rr_sweep_kernel<2>;
-    default: return rr::rr_sweep_kernel<4>;
+    if (c.TH == 128) {
+        switch (c.S) {
+        case 1: return rr::rr_sweep_kernel<1, 128, SP>;
+        case 2: return rr::rr_sweep_kernel<2, 128, SP>;
+        case 4: return rr::rr_sweep_kernel<4, 128, SP>;
+        default: return rr::rr_sweep_kernel<8, 128, SP>;
+        }
     }
+    switch (c.S) {
+    case 1: return rr::rr_sweep_kernel<1, 256, SP>;
+    case 2: return rr::rr_sweep_kernel<2, 256, SP>;
+    default: return rr::rr_sweep_kernel<4, 256, SP>;
+    }
+}
+SweepKernel sweep_kernel_for(const SweepCfg &c, bool special)
+{
+    return special ? sweep_kernel_sel<true>(c) : sweep_kernel_sel<false>(c);
 }
 
 // grid.x of a sweep for a plan with n_chunks chunks
-int sweep_gx(rr_engine *e, int S, size_t smem, int n_chunks, int n_tiles)
+int sweep_gx(rr_engine *e, const SweepCfg &c, bool special, size_t smem, int n_chunks, int n_tiles)
 {
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel_for(S), rr::kSweepThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel_for(c, special), c.TH, smem);
     occ = std::max(1, occ);
     const int slots = e->sm_count * occ;
     int gx = std::max(1, slots / std::max(1, n_chunks));
@@ -268,28 +307,33 @@ int sweep_gx(rr_engine *e, int S, size_t smem, int n_chunks, int n_tiles)
 
 // Runs one plan: zero accumulators, launch the interpreter, reduce rows into `dots` (device),
 // all-reduce across ranks when sharded. dd: the plan holds DOTDD reductions only.
-int run_sweep(rr_engine *e, const rr::SweepPlan &P, int S, DevBuf &dots, bool dd, double *stg, int64_t ld_stg)
+int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf &dots, bool dd, double *stg, int64_t ld_stg)
 {
     if (P.chunks.empty()) return RR_OK;
-    const int T = rr::kSweepThreads * S;
+    const int T = cfg.T();
+    const int NW = cfg.TH / 32;
     const int n_tiles = (int)((e->n + T - 1) / T);
-    const size_t smem = (size_t)P.max_tile_cols * T * 8;
-    if (smem > kSmemBudget) return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
-    SweepKernel kern = sweep_kernel_for(S);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    // one extra column: the per-thread scratch the out-of-line operators work on
+    const size_t smem = (size_t)(P.max_tile_cols + 1) * T * 8;
+    if (smem > cfg.dyn_smem_budget()) return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
+    bool special = dd;
+    for (const RRIns &x : P.ins)
+        if (RR_OP(x.w0) == RI_CLSMET) { special = true; break; }
+    SweepKernel kern = sweep_kernel_for(cfg, special);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemPerBlockMax - rr::kSweepStaticSmem)));
     const int n_chunks = (int)P.chunks.size();
-    int gx = sweep_gx(e, S, smem, n_chunks, std::max(1, n_tiles));
+    int gx = sweep_gx(e, cfg, special, smem, n_chunks, std::max(1, n_tiles));
     const int64_t stride = round_up(std::max(P.n_dots, 1), 32) + 32;
     // keep the accumulator rows within a sane budget
     const size_t row_budget = (size_t)env_double("RR_B200_ACC_BYTES", 6e9);
-    while (gx > 1 && (size_t)gx * rr::kSweepWarps * stride * 8 > row_budget) gx = (gx + 1) / 2;
-    const int rows = gx * rr::kSweepWarps;
+    while (gx > 1 && (size_t)gx * NW * stride * 8 > row_budget) gx = (gx + 1) / 2;
+    const int rows = gx * NW;
 
-    // instruction stream is padded with one extra END (the kernel prefetches one ahead)
+    // the kernel streams whole windows of kInsWindow instructions: pad the tail with ENDs
     std::vector<RRIns> ins(P.ins);
     RRIns endi;
     std::memset(&endi, 0, sizeof(endi));
-    ins.push_back(endi);
+    ins.resize(P.ins.size() + rr::kInsWindow, endi);
     int rc;
     if ((rc = upload(e, e->d_ins, ins.data(), ins.size()))) return rc;
     if ((rc = upload(e, e->d_chunks, P.chunks.data(), P.chunks.size()))) return rc;
@@ -314,7 +358,7 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, int S, DevBuf &dots, bool dd
     a.ld_stg = ld_stg;
     a.n_tiles = n_tiles;
     CU(cudaEventRecord(e->ev[2], e->stream));
-    kern<<<dim3(gx, n_chunks), rr::kSweepThreads, smem, e->stream>>>(a);
+    kern<<<dim3(gx, n_chunks), cfg.TH, smem, e->stream>>>(a, P.max_tile_cols);
     CU(cudaGetLastError());
     CU(cudaEventRecord(e->ev[3], e->stream));
     e->stats.sweep_launches++;
@@ -360,15 +404,16 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, int S, DevBuf &dots, bool dd
     return RR_OK;
 }
 
-rr::PlanLimits limits_for(rr_engine *e, int S, int n_cand)
+rr::PlanLimits limits_for(rr_engine *e, const SweepCfg &cfg, int n_cand)
 {
     rr::PlanLimits lim;
-    lim.tile_cols = std::min(tile_cols_for(S), 0x7000);
+    lim.tile_cols = cfg.tile_cols();
+    if (e->slots_pref > 0) lim.max_slots = e->slots_pref;
     lim.no_cse = (e->flags & RR_FLAG_NO_CSE) != 0;
-    const int T = rr::kSweepThreads * S;
+    const int T = cfg.T();
     const int n_tiles = (int)std::max<int64_t>(1, (e->n + T - 1) / T);
     // enough independent program chunks to occupy the GPU when there are few sample tiles
-    const int want_blocks = e->sm_count * 2;
+    const int want_blocks = e->sm_count * std::max(2, cfg.occ);
     lim.target_chunks = n_tiles >= want_blocks ? 1 : std::min(std::max(1, n_cand), (want_blocks + n_tiles - 1) / n_tiles);
     return lim;
 }
@@ -450,6 +495,11 @@ int create_common(const double *Xsrc, const double *y, int64_t n, int32_t d, int
     e->ld = round_up(n, kLdAlign);
     e->exact_max_n = env_int("RR_B200_EXACT_MAX_N", 4096);
     e->s_pref = env_int("RR_B200_S", 0);
+    e->th_pref = env_int("RR_B200_TH", 0);
+    e->occ_pref = env_int("RR_B200_OCC", 0);
+    e->slots_pref = env_int("RR_B200_SLOTS", 0);
+    if (e->th_pref != 128 && e->th_pref != 256) e->th_pref = 0;
+    if (e->s_pref != 1 && e->s_pref != 2 && e->s_pref != 4 && !(e->s_pref == 8 && e->th_pref == 128)) e->s_pref = 0;
     auto bail = [&](int code) {
         g_thread_error = e->error;
         e->free_all();
@@ -524,7 +574,7 @@ int download_results(rr_engine *e, const rr_batch *b, rr_result *res, bool with_
 // ---- EVAL_ONLY ------------------------------------------------------------------------------
 int run_eval(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *res)
 {
-    const int S = choose_S(e);
+    const SweepCfg S = choose_cfg(e);
     rr::PlanLimits lim = limits_for(e, S, b->n_cand);
     rr::ColIds cols{e->d, e->d + 1};
     rr::SweepPlan P;
@@ -550,7 +600,7 @@ int run_eval(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
 // ---- OLS_FIT, exact path ----------------------------------------------------------------------
 int run_exact(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *res)
 {
-    const int S = choose_S(e);
+    const SweepCfg S = choose_cfg(e);
     rr::PlanLimits lim = limits_for(e, S, bp.n_terms_distinct());
     rr::ColIds cols{e->d, e->d + 1};
     rr::SweepPlan P;
@@ -623,7 +673,7 @@ int run_exact(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *
 // ---- OLS_FIT, Gram path -----------------------------------------------------------------------
 int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *res)
 {
-    const int S = choose_S(e);
+    const SweepCfg S = choose_cfg(e);
     const int nc = b->n_cand;
     const int n_terms = b->cand_term_begin[nc];
     const int n_coef = n_terms + nc;
@@ -948,7 +998,7 @@ int rr_classifier_metrics(rr_engine *e, const rr_batch *b, double *accuracy, dou
     rr::BatchPlanner bp(b, e->d);
     std::string err = bp.analyse((e->flags & RR_FLAG_NO_CSE) != 0);
     if (!err.empty()) return e->fail(RR_ERR_INVALID, "malformed batch: " + err);
-    const int S = choose_S(e);
+    const SweepCfg S = choose_cfg(e);
     rr::PlanLimits lim = limits_for(e, S, b->n_cand);
     rr::ColIds cols{e->d, e->d + 1};
     rr::SweepPlan P;
@@ -993,7 +1043,7 @@ static int predict_common(rr_engine *e, const uint32_t *code, int32_t code_len, 
     rr::BatchPlanner bp(&b, d);
     std::string err = bp.analyse(true);
     if (err.empty()) {
-        const int S = choose_S(t);
+        const SweepCfg S = choose_cfg(t);
         rr::PlanLimits lim = limits_for(t, S, 1);
         lim.target_chunks = 1;
         rr::SweepPlan P;

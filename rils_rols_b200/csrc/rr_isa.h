@@ -10,77 +10,75 @@
 //
 // Each node of node::evaluate_inner (/root/reference/rils_rols_cpp/node.cpp:23-95) maps
 // to one instruction with IEEE-identical operand order; leaves are folded into their
-// parent as an operand (COL or CONST), so about half of the reference's node evaluations
-// cost no instruction at all.
+// parent as an operand (tile column or immediate), so about half of the reference's node
+// evaluations cost no instruction at all.
+//
+// Opcodes are dense (one jump table in the kernel) and specialised by operand kind
+// (_C immediate, _M tile column) and operand order (R* = reversed: t = src op t), so a
+// dispatched case does no further flag tests.
 #ifndef RR_ISA_H
 #define RR_ISA_H
 
 #include <stdint.h>
 
 struct RRIns {
-    uint32_t w0;  // opcode | flags
-    uint32_t w1;  // tile column index (operand / destination) or packed DOT operands
-    double imm;   // constant operand / AXPY coefficient
+    uint32_t w0;  // opcode | aux << 8
+    uint32_t w1;  // tile column index (operand / destination) or packed MDOT partners
+    double imm;   // constant operand / AXPY coefficient / packed MDOT partners
 };
 static_assert(sizeof(RRIns) == 16, "RRIns must be 16 bytes");
 
 enum RRInsOp : uint32_t {
     RI_END = 0,
-    RI_LOAD,   // t = src
-    RI_ST,     // tile[w1] = t
-    RI_STG,    // out[w1][sample] = t   (materialise a column in global memory)
-    // binary: t = t op src   (RF_SWAP: t = src op t)
-    RI_ADD,
-    RI_SUB,
-    RI_MUL,
-    RI_DIV,
-    RI_POW,
-    RI_LT,
-    RI_GT,
-    RI_EQ,
-    RI_NE,
-    RI_MIN,
-    RI_MAX,
-    RI_AXPY,   // t = t + imm * tile[w1]   (product rounded, then sum: the c*term + ... chain of
-               //                           rils_rols_cpp.cpp:503-510)
-    // unary: t = f(t)
-    RI_SIN,
-    RI_COS,
-    RI_LN,
-    RI_EXP,
-    RI_SQRT,
-    RI_SQR,
-    // reductions over the samples: out[dot_id] += sum_s a_s * b_s ; dot ids are implicit,
-    // consecutive in program order from the chunk's dot_base
-    RI_DOT,
-    RI_DOTDD,  // same, accumulated in double-double (two outputs: hi, lo)
-    // classifier metrics of t (rils_rols_cpp.cpp:51-86): three consecutive dot outputs
+    RI_LOAD_C,  // t = imm
+    RI_LOAD_M,  // t = tile[w1]
+    RI_ST,      // tile[w1] = t
+    RI_STG,     // out[w1][sample] = t   (materialise a column in global memory)
+    RI_ADD_C, RI_ADD_M,    // t = t + src
+    RI_SUB_C, RI_SUB_M,    // t = t - src
+    RI_RSUB_C, RI_RSUB_M,  // t = src - t
+    RI_MUL_C, RI_MUL_M,    // t = t * src
+    RI_DIV_C, RI_DIV_M,    // t = t / src
+    RI_RDIV_C, RI_RDIV_M,  // t = src / t
+    RI_AXPY,    // t = t + imm * tile[w1]  (product rounded, then sum: the c*term + ... chain of
+                //                          rils_rols_cpp.cpp:503-510)
+    RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR,  // t = f(t)
+    // rarely generated operators share one case: aux = RRRareOp | RB_CONST | RB_SWAP
+    RI_RARE,
+    // Reductions over the samples with a = t: aux bit 0 = also t.t, bit 1 = also sum(t),
+    // bits 8-15 (of aux) = number of tile-column partners (<= 6, 16-bit column indices packed in
+    // w1 and imm). Outputs in that order, ids implicit and consecutive from the chunk's dot_base.
+    RI_MDOT,
+    RI_MDOTDD,  // same, accumulated in double-double (two outputs per reduction: hi, lo)
+    // classifier metrics of t against y = tile[w1] (rils_rols_cpp.cpp:51-86): three outputs
     RI_CLSMET,
     RI_OPCOUNT
 };
 
-// w0 layout: bits 0-7 opcode, bit 8 RF_CONST (operand is imm, else tile column w1),
-// bit 9 RF_SWAP. DOT: bits 8-9 = kind of a, bits 10-11 = kind of b;
-// w1 = a column | b column << 16.
+enum RRRareOp : uint32_t { RR_POW = 0, RR_LT, RR_GT, RR_EQ, RR_NE, RR_MIN, RR_MAX };
 enum : uint32_t {
-    RF_CONST = 1u << 8,
-    RF_SWAP = 1u << 9,
+    RB_CONST = 1u << 4,  // operand is imm, else tile[w1]
+    RB_SWAP = 1u << 5,   // t = src op t
+    MD_SELF = 1u << 0,
+    MD_ONE = 1u << 1,
+    MD_MAX_PARTNERS = 6,
 };
-enum RRDotKind : uint32_t { RD_COL = 0, RD_ONE = 1, RD_TOS = 2 };
-#define RR_DOT_W0(op, ka, kb) ((uint32_t)(op) | ((uint32_t)(ka) << 8) | ((uint32_t)(kb) << 10))
-#define RR_DOT_KA(w0) (((w0) >> 8) & 3u)
-#define RR_DOT_KB(w0) (((w0) >> 10) & 3u)
+#define RR_W0(op, aux) ((uint32_t)(op) | ((uint32_t)(aux) << 8))
+#define RR_OP(w0) ((w0) & 0xffu)
+#define RR_AUX(w0) ((w0) >> 8)
+#define RR_MDOT_COUNT(w0) (((w0) >> 16) & 0xffu)
 
 // One independently schedulable piece of a sweep: its own staged columns, slot state and
 // dot range. Large-n sweeps use one chunk (maximal sharing); small-n sweeps are cut into
 // many chunks so that every SM has work.
 struct RRChunk {
-    int32_t pc_begin;   // first instruction (the chunk ends with RI_END)
+    int32_t pc_begin;   // first instruction; the chunk ends with RI_END
+    int32_t n_ins;      // instructions including the RI_END
     int32_t dot_base;   // first dot output id
-    int32_t n_dots;     // dot outputs of this chunk (DOTDD counts 2, CLSMET counts 3)
+    int32_t n_dots;     // dot outputs of this chunk (MDOTDD outputs count 2, CLSMET 3)
     int32_t col_begin;  // into the plan's staged-column list
     int32_t n_cols;     // staged global columns; slots follow them in the tile
-    int32_t reserved[3];
+    int32_t reserved[2];
 };
 static_assert(sizeof(RRChunk) == 32, "RRChunk must be 32 bytes");
 

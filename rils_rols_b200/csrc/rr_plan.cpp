@@ -30,22 +30,27 @@ int arity(uint32_t op)  // == get_arity, /root/reference/rils_rols_cpp/node.h:40
     }
 }
 
-uint32_t bin_ins(uint32_t op)
+// binary node -> specialised opcode for operand kind (konst) and order (swap: t = src op t)
+uint32_t bin_ins(uint32_t op, bool konst, bool swap)
 {
+    const uint32_t k = konst ? 0u : 1u;  // _C opcodes precede their _M twins
     switch (op) {
-    case RR_OP_PLUS: return RI_ADD;
-    case RR_OP_MINUS: return RI_SUB;
-    case RR_OP_MULTIPLY: return RI_MUL;
-    case RR_OP_DIVIDE: return RI_DIV;
-    case RR_OP_POW: return RI_POW;
-    case RR_OP_LESS_THAN: return RI_LT;
-    case RR_OP_GREATER_THAN: return RI_GT;
-    case RR_OP_EQUAL: return RI_EQ;
-    case RR_OP_NOT_EQUAL: return RI_NE;
-    case RR_OP_MIN: return RI_MIN;
-    case RR_OP_MAX: return RI_MAX;
+    case RR_OP_PLUS: return RR_W0(RI_ADD_C + k, 0);
+    case RR_OP_MULTIPLY: return RR_W0(RI_MUL_C + k, 0);
+    case RR_OP_MINUS: return RR_W0((swap ? RI_RSUB_C : RI_SUB_C) + k, 0);
+    case RR_OP_DIVIDE: return RR_W0((swap ? RI_RDIV_C : RI_DIV_C) + k, 0);
     }
-    return RI_END;
+    uint32_t rare = 0;
+    switch (op) {
+    case RR_OP_POW: rare = RR_POW; break;
+    case RR_OP_LESS_THAN: rare = RR_LT; break;
+    case RR_OP_GREATER_THAN: rare = RR_GT; break;
+    case RR_OP_EQUAL: rare = RR_EQ; break;
+    case RR_OP_NOT_EQUAL: rare = RR_NE; break;
+    case RR_OP_MIN: rare = RR_MIN; break;
+    case RR_OP_MAX: rare = RR_MAX; break;
+    }
+    return RR_W0(RI_RARE, rare | (konst ? RB_CONST : 0u) | (swap ? RB_SWAP : 0u));
 }
 
 uint32_t un_ins(uint32_t op)
@@ -191,6 +196,8 @@ struct BatchPlanner::Chunk {
     std::vector<uint64_t> slot_stamp;
     std::vector<uint64_t> slot_pin;
     std::unordered_map<int32_t, int32_t> term_slot;
+    std::vector<std::vector<uint32_t>> mdot_refs;  // pre-patch partner refs of each MDOT
+    std::vector<size_t> mdot_at;                   // ... and its instruction index
     uint64_t clock = 1, epoch = 1;
     std::string err;
 
@@ -204,7 +211,7 @@ struct BatchPlanner::Chunk {
             colmap.emplace(g, (int32_t)colmap.size());
             P.cols.push_back(g);
         }
-        pool_cap = lim.tile_cols - (int32_t)cols.size();
+        pool_cap = std::min(lim.tile_cols - (int32_t)cols.size(), lim.max_slots);
     }
 
     uint32_t staged(int32_t gcol)
@@ -271,8 +278,8 @@ struct BatchPlanner::Chunk {
     void gen(const Term &T, int32_t x)
     {
         const TermNode &n = T.nodes[x];
-        if (n.op == RR_OP_CONST) { emit(RI_LOAD | RF_CONST, 0, n.cval, 0); return; }
-        if (n.op == RR_OP_VAR) { emit(RI_LOAD, staged(n.var), 0.0, 0); return; }
+        if (n.op == RR_OP_CONST) { emit(RI_LOAD_C, 0, n.cval, 0); return; }
+        if (n.op == RR_OP_VAR) { emit(RI_LOAD_M, staged(n.var), 0.0, 0); return; }
         const int ar = arity(n.op);
         if (ar == 1) {
             gen(T, n.left);
@@ -280,30 +287,29 @@ struct BatchPlanner::Chunk {
             return;
         }
         const TermNode &L = T.nodes[n.left], &R = T.nodes[n.right];
-        const uint32_t op = bin_ins(n.op);
-        auto leaf_operand = [&](const TermNode &lf, uint32_t extra) {
-            if (lf.op == RR_OP_CONST) emit(op | RF_CONST | extra, 0, lf.cval, kW[n.op]);
-            else emit(op | extra, staged(lf.var), 0.0, kW[n.op]);
+        auto leaf_operand = [&](const TermNode &lf, bool swap) {
+            if (lf.op == RR_OP_CONST) emit(bin_ins(n.op, true, swap), 0, lf.cval, kW[n.op]);
+            else emit(bin_ins(n.op, false, swap), staged(lf.var), 0.0, kW[n.op]);
         };
         if (R.leaf()) {
             gen(T, n.left);
-            leaf_operand(R, 0);
+            leaf_operand(R, false);
         } else if (L.leaf()) {
             gen(T, n.right);
-            leaf_operand(L, RF_SWAP);
+            leaf_operand(L, true);
         } else if (L.need >= R.need) {
             gen(T, n.left);
             const int32_t s = alloc_slot(-2);
             emit(RI_ST, (uint32_t)s, 0.0, 0);
             gen(T, n.right);
-            emit(op | RF_SWAP, (uint32_t)s, 0.0, kW[n.op]);  // t = L(slot) op R(t)
+            emit(bin_ins(n.op, false, true), (uint32_t)s, 0.0, kW[n.op]);  // t = L(slot) op R(t)
             free_slot(s);
         } else {
             gen(T, n.right);
             const int32_t s = alloc_slot(-2);
             emit(RI_ST, (uint32_t)s, 0.0, 0);
             gen(T, n.left);
-            emit(op, (uint32_t)s, 0.0, kW[n.op]);  // t = L(t) op R(slot)
+            emit(bin_ins(n.op, false, false), (uint32_t)s, 0.0, kW[n.op]);  // t = L(t) op R(slot)
             free_slot(s);
         }
     }
@@ -315,24 +321,64 @@ struct BatchPlanner::Chunk {
         P.n_term_evals++;
     }
 
-    // make term u resident in a slot; returns slot, sets tos = true when t holds its value
-    int32_t ensure(int32_t u, bool &tos)
+    // make term u resident in a slot AND leave its value in t; returns the slot
+    int32_t ensure_tos(int32_t u)
     {
         int32_t s = lookup(u);
-        if (s >= 0) { tos = false; return s; }
+        if (s >= 0) {
+            emit(RI_LOAD_M, (uint32_t)s, 0.0, 0);
+            return s;
+        }
         gen_term(u);
         s = alloc_slot(u);
         emit(RI_ST, (uint32_t)s, 0.0, 0);
-        tos = true;
+        return s;
+    }
+    // make term u resident (t is clobbered when it has to be evaluated)
+    int32_t ensure(int32_t u)
+    {
+        int32_t s = lookup(u);
+        if (s >= 0) return s;
+        gen_term(u);
+        s = alloc_slot(u);
+        emit(RI_ST, (uint32_t)s, 0.0, 0);
         return s;
     }
 
-    int32_t dot(uint32_t op, uint32_t ka, uint32_t a, uint32_t kb, uint32_t b)
+    // Reductions of t against itself / ones / tile columns (pre-patch column refs). Appends the
+    // output ids in the order self, one, partners...; dd outputs take two ids each.
+    void mdot(bool self, bool one, const std::vector<uint32_t> &partners, bool dd, std::vector<int32_t> &ids)
     {
-        emit(RR_DOT_W0(op, ka, kb), (a & 0xffffu) | ((b & 0xffffu) << 16), 0.0, op == RI_DOTDD ? 10.0 : 1.0);
+        const int step = dd ? 2 : 1;
+        size_t done = 0;
+        bool first = true;
+        do {
+            const size_t take = std::min<size_t>(MD_MAX_PARTNERS, partners.size() - done);
+            uint32_t aux = 0;
+            int n_out = (int)take;
+            if (first && self) { aux |= MD_SELF; ++n_out; }
+            if (first && one) { aux |= MD_ONE; ++n_out; }
+            aux |= (uint32_t)take << 8;
+            if (n_out > 0) {
+                mdot_at.push_back(P.ins.size());
+                mdot_refs.emplace_back(partners.begin() + done, partners.begin() + done + take);
+                emit(RR_W0(dd ? RI_MDOTDD : RI_MDOT, aux), 0, 0.0, (dd ? 10.0 : 1.0) * n_out);
+                for (int i = 0; i < n_out; ++i) {
+                    ids.push_back(P.n_dots);
+                    P.n_dots += step;
+                }
+                P.n_dot_ins += n_out;
+            }
+            done += take;
+            first = false;
+        } while (done < partners.size());
+    }
+    int32_t clsmet(uint32_t y_ref)
+    {
+        emit(RI_CLSMET, y_ref, 0.0, 60);
         const int32_t id = P.n_dots;
-        P.n_dots += op == RI_DOTDD ? 2 : (op == RI_CLSMET ? 3 : 1);
-        P.n_dot_ins++;
+        P.n_dots += 3;
+        P.n_dot_ins += 3;
         return id;
     }
 
@@ -343,19 +389,32 @@ struct BatchPlanner::Chunk {
         auto patch = [&](uint32_t v) -> uint32_t { return (v & STAGED) ? (v & 0x7fffu) : (uint32_t)n_cols + v; };
         for (size_t i = pc_begin; i < P.ins.size(); ++i) {
             RRIns &x = P.ins[i];
-            const uint32_t op = x.w0 & 0xffu;
-            if (op == RI_DOT || op == RI_DOTDD || op == RI_CLSMET) {
-                uint32_t a = x.w1 & 0xffffu, b = x.w1 >> 16;
-                if (RR_DOT_KA(x.w0) == RD_COL) a = patch(a);
-                if (RR_DOT_KB(x.w0) == RD_COL) b = patch(b);
-                x.w1 = a | (b << 16);
-            } else if (op == RI_ST || op == RI_AXPY || (op >= RI_LOAD && op <= RI_MAX && op != RI_STG && !(x.w0 & RF_CONST))) {
-                x.w1 = patch(x.w1);
+            bool has_col = false;
+            switch (RR_OP(x.w0)) {
+            case RI_LOAD_M: case RI_ST: case RI_ADD_M: case RI_SUB_M: case RI_RSUB_M: case RI_MUL_M:
+            case RI_DIV_M: case RI_RDIV_M: case RI_AXPY: case RI_CLSMET:
+                has_col = true;
+                break;
+            case RI_RARE:
+                has_col = !(RR_AUX(x.w0) & RB_CONST);
+                break;
+            default:
+                break;
             }
+            if (has_col) x.w1 = patch(x.w1);
+        }
+        for (size_t k = 0; k < mdot_at.size(); ++k) {
+            RRIns &x = P.ins[mdot_at[k]];
+            uint16_t p[MD_MAX_PARTNERS] = {0, 0, 0, 0, 0, 0};
+            for (size_t j = 0; j < mdot_refs[k].size(); ++j) p[j] = (uint16_t)patch(mdot_refs[k][j]);
+            x.w1 = (uint32_t)p[0] | ((uint32_t)p[1] << 16);
+            const uint64_t hi = (uint64_t)p[2] | ((uint64_t)p[3] << 16) | ((uint64_t)p[4] << 32) | ((uint64_t)p[5] << 48);
+            std::memcpy(&x.imm, &hi, 8);
         }
         RRChunk c;
         std::memset(&c, 0, sizeof(c));
         c.pc_begin = pc_begin;
+        c.n_ins = (int32_t)P.ins.size() - pc_begin;
         c.dot_base = dot_base;
         c.n_dots = P.n_dots - dot_base;
         c.col_begin = col_begin;
@@ -471,7 +530,6 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
     std::string err = cut_chunks(*this, units, lim, {cols.yc}, min_slots, specs);
     if (!err.empty()) return err;
 
-    const uint32_t DOP = dd ? RI_DOTDD : RI_DOT;
     cand_dot.clear();
     cand_dot_begin.assign(1, 0);
     // dot key -> id, global over the plan (a dot computed in an earlier chunk is simply reused)
@@ -481,46 +539,53 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
         if (a > b) std::swap(a, b);
         return ((uint64_t)(uint32_t)(int32_t)a << 32) | (uint64_t)(uint32_t)(int32_t)b;
     };
+    std::vector<uint32_t> partners;
+    std::vector<uint64_t> pkeys;
+    std::vector<int32_t> ids;
     for (const ChunkSpec &cs : specs) {
         Chunk ch(*this, P, lim, cs.cols);
         const uint32_t yc_col = ch.staged(cols.yc);
         for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
             const std::vector<int32_t> &T = units[ui].terms;
             const int32_t m = (int32_t)T.size();
-            // which distinct terms take part in a dot that is still missing
-            std::vector<int32_t> N;
             auto missing = [&](int64_t a, int64_t b) { return dots.find(key(a, b)) == dots.end(); };
+            // distinct terms that take part in a reduction that is still missing; a missing pair has
+            // both ends in N (missing() is symmetric), so processing N in order emits each pair once,
+            // when its later term is in t
+            std::vector<int32_t> N;
             for (int32_t i = 0; i < m; ++i) {
                 bool miss = missing(T[i], KEY_YC) || missing(T[i], KEY_ONE);
                 for (int32_t j = 0; j < m && !miss; ++j) miss = missing(T[i], T[j]);
                 if (miss && std::find(N.begin(), N.end(), T[i]) == N.end()) N.push_back(T[i]);
             }
             ch.unpin_all();
-            const int32_t tmp_need = need + 1;
-            const int32_t room = ch.pool_cap - tmp_need;
+            const int32_t room = ch.pool_cap - (need + 1);
             if (room < 2) return "tile too small";
-            auto pair_dots = [&](int32_t u, bool tos, int32_t su, const std::vector<int32_t> &done) {
-                // dots of u with itself, yc, ones and every already-resident partner
-                const uint32_t ka = tos ? RD_TOS : RD_COL;
-                if (missing(u, u)) dots[key(u, u)] = ch.dot(DOP, ka, su, ka, su);
-                if (missing(u, KEY_YC)) dots[key(u, KEY_YC)] = ch.dot(DOP, ka, su, RD_COL, yc_col);
-                if (missing(u, KEY_ONE)) dots[key(u, KEY_ONE)] = ch.dot(DOP, ka, su, RD_ONE, 0);
+            // t = u; reductions of u with itself, ones, yc and every partner already resident
+            auto reduce_term = [&](int32_t u, const std::vector<int32_t> &done) {
+                ch.ensure_tos(u);
+                const bool self = missing(u, u), one = missing(u, KEY_ONE);
+                partners.clear();
+                pkeys.clear();
+                if (missing(u, KEY_YC)) { partners.push_back(yc_col); pkeys.push_back(key(u, KEY_YC)); }
                 for (int32_t v : done) {
                     if (v == u || !missing(u, v)) continue;
-                    // only pairs that some candidate of this unit needs
                     const int32_t sv = ch.lookup(v);
                     if (sv < 0) { ch.err = "internal: partner not resident"; return; }
-                    dots[key(u, v)] = ch.dot(DOP, ka, su, RD_COL, (uint32_t)sv);
+                    partners.push_back((uint32_t)sv);
+                    pkeys.push_back(key(u, v));
                 }
+                ids.clear();
+                ch.mdot(self, one, partners, dd, ids);
+                size_t q = 0;
+                if (self) dots[key(u, u)] = ids[q++];
+                if (one) dots[key(u, KEY_ONE)] = ids[q++];
+                for (uint64_t k : pkeys) dots[k] = ids[q++];
             };
             if ((int32_t)N.size() <= room) {
-                // a missing pair has both ends in N (missing() is symmetric), so processing N in
-                // order emits each pair once, when its later term becomes resident
                 std::vector<int32_t> done;
                 for (int32_t u : N) {
-                    bool tos = false;
-                    const int32_t su = ch.ensure(u, tos);
-                    pair_dots(u, tos, su, done);
+                    reduce_term(u, done);
                     done.push_back(u);
                     if (!ch.err.empty()) return ch.err;
                 }
@@ -532,17 +597,13 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
                     for (int32_t gb = ga; gb < ng; ++gb) {
                         ch.unpin_all();
                         std::vector<int32_t> done;
-                        for (int32_t grp : {ga, gb}) {
+                        for (int32_t pass = 0; pass < (ga == gb ? 1 : 2); ++pass) {
+                            const int32_t grp = pass == 0 ? ga : gb;
                             for (int32_t i = grp * g; i < std::min((grp + 1) * g, (int32_t)N.size()); ++i) {
-                                const int32_t u = N[i];
-                                if (std::find(done.begin(), done.end(), u) != done.end()) continue;
-                                bool tos = false;
-                                const int32_t su = ch.ensure(u, tos);
-                                pair_dots(u, tos, su, done);
-                                done.push_back(u);
+                                reduce_term(N[i], done);
+                                done.push_back(N[i]);
                                 if (!ch.err.empty()) return ch.err;
                             }
-                            if (ga == gb) break;
                         }
                     }
             }
@@ -583,6 +644,8 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
     if (!err.empty()) return err + " (residual pass)";
     cand_dot.clear();
     cand_dot_begin.assign(1, 0);
+    std::vector<uint32_t> partners;
+    std::vector<int32_t> ids;
     for (const ChunkSpec &cs : specs) {
         Chunk ch(*this, P, lim, cs.cols);
         const uint32_t y_col = ch.staged(cols.y);
@@ -594,8 +657,7 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
             ch.unpin_all();
             std::vector<int32_t> slot(m);
             for (int32_t i = 0; i < m; ++i) {
-                bool tos;
-                slot[i] = ch.ensure(T[i], tos);
+                slot[i] = ch.ensure(T[i]);
                 if (!ch.err.empty()) return ch.err;
             }
             // yhat in the association order of rils_rols_cpp.cpp:488-515
@@ -604,25 +666,29 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
                 const double ci = cf[i];
                 if (ci == 0.0) continue;  // snapped away (value_zero)
                 if (first) {
-                    ch.emit(RI_LOAD, (uint32_t)slot[i], 0.0, 0);
-                    if (ci != 1.0) ch.emit(RI_MUL | RF_CONST | RF_SWAP, 0, ci, 1);
+                    ch.emit(RI_LOAD_M, (uint32_t)slot[i], 0.0, 0);
+                    if (ci != 1.0) ch.emit(RI_MUL_C, 0, ci, 1);
                     first = false;
                 } else if (ci == 1.0) {
-                    ch.emit(RI_ADD, (uint32_t)slot[i], 0.0, 1);
+                    ch.emit(RI_ADD_M, (uint32_t)slot[i], 0.0, 1);
                 } else {
                     ch.emit(RI_AXPY, (uint32_t)slot[i], ci, 2);
                 }
             }
             if (cf[m] != 0.0) {
-                if (first) ch.emit(RI_LOAD | RF_CONST, 0, cf[m], 0);
-                else ch.emit(RI_ADD | RF_CONST, 0, cf[m], 1);
+                if (first) ch.emit(RI_LOAD_C, 0, cf[m], 0);
+                else ch.emit(RI_ADD_C, 0, cf[m], 1);
                 first = false;
             }
-            if (first) ch.emit(RI_LOAD | RF_CONST, 0, 0.0, 0);
-            ch.emit(RI_SUB | RF_SWAP, y_col, 0.0, 1);  // t = y - yhat
-            cand_dot.push_back(ch.dot(RI_DOT, RD_TOS, 0, RD_TOS, 0));
-            for (int32_t i = 0; i < m; ++i) cand_dot.push_back(ch.dot(RI_DOT, RD_TOS, 0, RD_COL, (uint32_t)slot[i]));
-            cand_dot.push_back(ch.dot(RI_DOT, RD_TOS, 0, RD_ONE, 0));
+            if (first) ch.emit(RI_LOAD_C, 0, 0.0, 0);
+            ch.emit(RI_RSUB_M, y_col, 0.0, 1);  // t = y - yhat
+            partners.clear();
+            for (int32_t i = 0; i < m; ++i) partners.push_back((uint32_t)slot[i]);
+            ids.clear();
+            ch.mdot(true, true, partners, false, ids);  // r.r, r.1, r.t_i
+            cand_dot.push_back(ids[0]);
+            for (int32_t i = 0; i < m; ++i) cand_dot.push_back(ids[2 + i]);
+            cand_dot.push_back(ids[1]);
             cand_dot_begin.push_back((int32_t)cand_dot.size());
         }
         if (!ch.err.empty()) return ch.err;
@@ -645,6 +711,7 @@ std::string BatchPlanner::plan_eval(const PlanLimits &lim, const ColIds &cols, b
     if (!err.empty()) return err;
     cand_dot.assign(b_->n_cand, DOT_NONE);
     std::unordered_map<int32_t, int32_t> done;  // identical programs share their result
+    std::vector<int32_t> ids;
     for (const ChunkSpec &cs : specs) {
         Chunk ch(*this, P, lim, cs.cols);
         const uint32_t y_col = ch.staged(cols.y);
@@ -656,10 +723,12 @@ std::string BatchPlanner::plan_eval(const PlanLimits &lim, const ColIds &cols, b
             ch.gen_term(u);
             int32_t id;
             if (metrics) {
-                id = ch.dot(RI_CLSMET, RD_TOS, 0, RD_COL, y_col);
+                id = ch.clsmet(y_col);
             } else {
-                ch.emit(RI_SUB | RF_SWAP, y_col, 0.0, 1);  // t = y - yhat
-                id = ch.dot(RI_DOT, RD_TOS, 0, RD_TOS, 0);
+                ch.emit(RI_RSUB_M, y_col, 0.0, 1);  // t = y - yhat
+                ids.clear();
+                ch.mdot(true, false, {}, false, ids);
+                id = ids[0];
             }
             done.emplace(u, id);
             cand_dot[c] = id;
@@ -697,3 +766,86 @@ std::string BatchPlanner::plan_materialise(const PlanLimits &lim, const ColIds &
 }
 
 }  // namespace rr
+
+// ---------------------------------------------------------------------------------------------
+// host-only tooling entry points (include/rr_b200.h)
+// ---------------------------------------------------------------------------------------------
+#include <cstdlib>
+
+namespace {
+template <typename T> T *dup_vec(const std::vector<T> &v)
+{
+    T *p = (T *)std::malloc(sizeof(T) * std::max<size_t>(v.size(), 1));
+    if (p && !v.empty()) std::memcpy(p, v.data(), sizeof(T) * v.size());
+    return p;
+}
+}  // namespace
+
+extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kind, int32_t tile_cols,
+                                   int32_t max_slots, int32_t target_chunks, int32_t no_cse,
+                                   const double *coef_snapped, rr_debug_plan *out)
+{
+    if (!batch || !out) return RR_ERR_INVALID;
+    std::memset(out, 0, sizeof(*out));
+    rr::BatchPlanner bp(batch, d);
+    std::string err = bp.analyse(no_cse != 0);
+    rr::SweepPlan P;
+    std::vector<int32_t> tab, tab_begin;
+    if (err.empty()) {
+        rr::PlanLimits lim;
+        lim.tile_cols = tile_cols;
+        if (max_slots > 0) lim.max_slots = max_slots;
+        lim.target_chunks = std::max(1, target_chunks);
+        lim.no_cse = no_cse != 0;
+        rr::ColIds cols{d, d + 1};
+        switch (kind) {
+        case 0: err = bp.plan_gram(lim, cols, nullptr, false, P, tab, tab_begin); break;
+        case 1: err = bp.plan_gram(lim, cols, nullptr, true, P, tab, tab_begin); break;
+        case 2: err = bp.plan_eval(lim, cols, false, P, tab); break;
+        case 3: err = bp.plan_eval(lim, cols, true, P, tab); break;
+        case 4: err = bp.plan_materialise(lim, cols, P); break;
+        case 5: {
+            if (!coef_snapped) { err = "residual plan needs coefficients"; break; }
+            std::vector<int32_t> all(batch->n_cand);
+            for (int32_t c = 0; c < batch->n_cand; ++c) all[c] = c;
+            err = bp.plan_residual(lim, cols, all, coef_snapped, P, tab, tab_begin);
+            break;
+        }
+        default: err = "bad kind";
+        }
+    }
+    if (!err.empty()) {
+        std::snprintf(out->error, sizeof(out->error), "%s", err.c_str());
+        return RR_ERR_INVALID;
+    }
+    out->n_ins = (int64_t)P.ins.size();
+    out->n_chunks = (int64_t)P.chunks.size();
+    out->n_cols = (int64_t)P.cols.size();
+    out->n_tab = (int64_t)tab.size();
+    out->n_tab_begin = (int64_t)tab_begin.size();
+    out->n_term_ids = (int64_t)bp.term_ids().size();
+    out->ins = dup_vec(P.ins);
+    out->chunks = dup_vec(P.chunks);
+    out->cols = dup_vec(P.cols);
+    out->tab = dup_vec(tab);
+    out->tab_begin = dup_vec(tab_begin);
+    out->term_ids = dup_vec(bp.term_ids());
+    out->n_dots = P.n_dots;
+    out->max_tile_cols = P.max_tile_cols;
+    out->n_terms_distinct = bp.n_terms_distinct();
+    out->w_issued = P.w_issued;
+    out->w_contract = bp.w_contract();
+    return RR_OK;
+}
+
+extern "C" void rr_debug_plan_free(rr_debug_plan *p)
+{
+    if (!p) return;
+    std::free(p->ins);
+    std::free(p->chunks);
+    std::free(p->cols);
+    std::free(p->tab);
+    std::free(p->tab_begin);
+    std::free(p->term_ids);
+    std::memset(p, 0, sizeof(*p));
+}

@@ -55,7 +55,7 @@ struct SweepPlan {
 
 struct PlanLimits {
     int32_t tile_cols = 56;  // columns that fit the shared-memory tile for the chosen tile height
-    int32_t tmp_slots = 8;   // spill temporaries reserved per chunk
+    int32_t max_slots = 1 << 20;  // cap on value slots (cached terms + temporaries) per chunk: bounds the tile
     int32_t target_chunks = 1;
     bool no_cse = false;
 };
