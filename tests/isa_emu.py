@@ -1,0 +1,163 @@
+"""CPU emulator of the engine's internal instruction set (rils_rols_b200/csrc/rr_isa.h).
+
+Test infrastructure: executes the instruction stream the planner produced (obtained through the
+host-only rr_debug_plan_batch entry point) with numpy, one n-vector per tile column, so the
+compiler half of the engine — term hashing, slot allocation, spills, fused reductions, chunking —
+can be checked against the oracle without a GPU. It is NOT a fallback of the product: nothing in
+rils_rols_b200/ imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from rils_rols_b200 import engine as E
+from rils_rols_b200.batch import Batch, rr_batch
+
+(RI_END, RI_LOAD_C, RI_LOAD_M, RI_ST, RI_STG, RI_ADD_C, RI_ADD_M, RI_SUB_C, RI_SUB_M, RI_RSUB_C, RI_RSUB_M,
+ RI_MUL_C, RI_MUL_M, RI_DIV_C, RI_DIV_M, RI_RDIV_C, RI_RDIV_M, RI_AXPY, RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT,
+ RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET) = range(28)
+RR_POW, RR_LT, RR_GT, RR_EQ, RR_NE, RR_MIN, RR_MAX = range(7)
+RB_CONST, RB_SWAP = 1 << 4, 1 << 5
+
+INS_DT = np.dtype([("w0", "<u4"), ("w1", "<u4"), ("imm", "<f8")])
+CHUNK_DT = np.dtype([("pc_begin", "<i4"), ("n_ins", "<i4"), ("dot_base", "<i4"), ("n_dots", "<i4"),
+                     ("col_begin", "<i4"), ("n_cols", "<i4"), ("r0", "<i4"), ("r1", "<i4")])
+
+KIND_GRAM, KIND_GRAM_DD, KIND_EVAL, KIND_EVAL_METRICS, KIND_MATERIALISE, KIND_RESIDUAL = range(6)
+
+
+class rr_debug_plan(C.Structure):
+    _fields_ = [("n_ins", C.c_int64), ("n_chunks", C.c_int64), ("n_cols", C.c_int64), ("n_tab", C.c_int64),
+                ("n_tab_begin", C.c_int64), ("n_term_ids", C.c_int64), ("ins", C.c_void_p), ("chunks", C.c_void_p),
+                ("cols", C.POINTER(C.c_int32)), ("tab", C.POINTER(C.c_int32)), ("tab_begin", C.POINTER(C.c_int32)),
+                ("term_ids", C.POINTER(C.c_int32)), ("n_dots", C.c_int32), ("max_tile_cols", C.c_int32),
+                ("n_terms_distinct", C.c_int32), ("reserved", C.c_int32), ("w_issued", C.c_double),
+                ("w_contract", C.c_double), ("error", C.c_char * 256)]
+
+
+class Plan:
+    def __init__(self, batch: Batch, d: int, kind: int, tile_cols: int = 56, max_slots: int = 0,
+                 target_chunks: int = 1, no_cse: bool = False, coef=None):
+        L = E.lib()
+        L.rr_debug_plan_batch.argtypes = [C.POINTER(rr_batch), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, C.POINTER(C.c_double), C.POINTER(rr_debug_plan)]
+        L.rr_debug_plan_batch.restype = C.c_int
+        L.rr_debug_plan_free.argtypes = [C.POINTER(rr_debug_plan)]
+        L.rr_debug_plan_free.restype = None
+        out = rr_debug_plan()
+        bs = batch.as_struct()
+        cp = None
+        if coef is not None:
+            coef = np.ascontiguousarray(coef, dtype=np.float64)
+            cp = coef.ctypes.data_as(C.POINTER(C.c_double))
+        rc = L.rr_debug_plan_batch(C.byref(bs), d, kind, tile_cols, max_slots, target_chunks, int(no_cse), cp,
+                                   C.byref(out))
+        if rc != 0:
+            raise ValueError(out.error.decode())
+
+        def arr(ptr, n, dt):
+            if n == 0:
+                return np.zeros(0, dtype=dt)
+            buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr if isinstance(ptr, int) else C.addressof(ptr.contents))
+            return np.frombuffer(buf, dtype=dt).copy()
+
+        self.ins = arr(out.ins, out.n_ins, INS_DT)
+        self.chunks = arr(out.chunks, out.n_chunks, CHUNK_DT)
+        self.cols = arr(out.cols, out.n_cols, np.int32)
+        self.tab = arr(out.tab, out.n_tab, np.int32)
+        self.tab_begin = arr(out.tab_begin, out.n_tab_begin, np.int32)
+        self.term_ids = arr(out.term_ids, out.n_term_ids, np.int32)
+        self.n_dots, self.max_tile_cols = out.n_dots, out.max_tile_cols
+        self.n_terms_distinct = out.n_terms_distinct
+        self.w_issued, self.w_contract = out.w_issued, out.w_contract
+        self.kind = kind
+        L.rr_debug_plan_free(C.byref(out))
+
+
+def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
+    """cols_global: (d+2, n) = features, y, y - mean(y). Returns (dots[n_dots], stg[n_stg, n])."""
+    n = cols_global.shape[1]
+    dots = np.zeros(max(plan.n_dots, 1))
+    stg = np.zeros((n_stg, n))
+    with np.errstate(all="ignore"):
+        for ch in plan.chunks:
+            ncols = int(ch["n_cols"])
+            tile = {i: cols_global[plan.cols[ch["col_begin"] + i]] for i in range(ncols)}
+            t = np.zeros(n)
+            out = int(ch["dot_base"])
+            pc = int(ch["pc_begin"])
+            end = pc + int(ch["n_ins"])
+            while pc < end:
+                w0, w1, imm = int(plan.ins["w0"][pc]), int(plan.ins["w1"][pc]), float(plan.ins["imm"][pc])
+                pc += 1
+                op, aux = w0 & 0xFF, w0 >> 8
+                assert w1 < plan.max_tile_cols or op in (RI_STG, RI_MDOT, RI_MDOTDD, RI_END, RI_LOAD_C) or (op % 2 == 1 and RI_ADD_C <= op <= RI_RDIV_C), \
+                    f"tile column {w1} out of range"
+                if op == RI_END:
+                    break
+                elif op == RI_LOAD_C: t = np.full(n, imm)
+                elif op == RI_LOAD_M: t = tile[w1].copy()
+                elif op == RI_ST: tile[w1] = t.copy()
+                elif op == RI_STG: stg[w1] = t
+                elif op == RI_ADD_C: t = t + imm
+                elif op == RI_ADD_M: t = t + tile[w1]
+                elif op == RI_SUB_C: t = t - imm
+                elif op == RI_SUB_M: t = t - tile[w1]
+                elif op == RI_RSUB_C: t = imm - t
+                elif op == RI_RSUB_M: t = tile[w1] - t
+                elif op == RI_MUL_C: t = t * imm
+                elif op == RI_MUL_M: t = t * tile[w1]
+                elif op == RI_DIV_C: t = t / imm
+                elif op == RI_DIV_M: t = t / tile[w1]
+                elif op == RI_RDIV_C: t = imm / t
+                elif op == RI_RDIV_M: t = tile[w1] / t
+                elif op == RI_AXPY: t = t + imm * tile[w1]
+                elif op == RI_SIN: t = np.sin(t)
+                elif op == RI_COS: t = np.cos(t)
+                elif op == RI_LN: t = np.log(t)
+                elif op == RI_EXP: t = np.exp(t)
+                elif op == RI_SQRT: t = np.sqrt(t)
+                elif op == RI_SQR: t = t * t
+                elif op == RI_RARE:
+                    u = np.full(n, imm) if aux & RB_CONST else tile[w1]
+                    x, v = (u, t) if aux & RB_SWAP else (t, u)
+                    r = aux & 0xF
+                    if r == RR_POW: t = np.power(x, v)
+                    elif r == RR_LT: t = (x < v).astype(float)
+                    elif r == RR_GT: t = (x > v).astype(float)
+                    elif r == RR_EQ: t = (x == v).astype(float)
+                    elif r == RR_NE: t = (x != v).astype(float)
+                    elif r == RR_MIN: t = np.where(x < v, x, v)
+                    else: t = np.where(x > v, x, v)
+                elif op in (RI_MDOT, RI_MDOTDD):
+                    step = 2 if op == RI_MDOTDD else 1
+                    vals = []
+                    if aux & 1: vals.append(float(np.dot(t, t)))
+                    if aux & 2: vals.append(float(np.sum(t)))
+                    npart = (aux >> 8) & 0xFF
+                    packed = w1 | (int(np.float64(imm).view(np.uint64)) << 32)
+                    for j in range(npart):
+                        c = (packed >> (16 * j)) & 0xFFFF
+                        vals.append(float(np.dot(t, tile[c])))
+                    for v in vals:
+                        dots[out] += v
+                        out += step
+                elif op == RI_CLSMET:
+                    y = tile[w1]
+                    ypb, yb = (t >= 0.5).astype(float), (y >= 0.5).astype(float)
+                    prob = 1.0 / (1.0 + np.exp(-2.0 * (t - 0.5)))
+                    dots[out] += float(np.sum(ypb == yb))
+                    dots[out + 1] += float(-np.sum((1.0 - yb) * np.log(1.0 - prob) + yb * np.log(prob)))
+                    dots[out + 2] += float(np.sum(np.abs(yb - t)))
+                    out += 3
+                else:
+                    raise AssertionError(f"bad opcode {op}")
+            assert out == int(ch["dot_base"]) + int(ch["n_dots"]), "chunk dot count mismatch"
+    return dots[: plan.n_dots], stg
+
+
+def engine_columns(X_rowmajor: np.ndarray, y: np.ndarray) -> np.ndarray:
+    Xfm = np.ascontiguousarray(np.asarray(X_rowmajor, dtype=np.float64).T)
+    return np.vstack([Xfm, y[None, :], (y - y.mean())[None, :]])

@@ -1,0 +1,212 @@
+"""CPU suite, part 2: the host half of the engine (no GPU, no compute through the C ABI).
+
+* librr_b200.so loads and exports every symbol include/rr_b200.h declares;
+* creating an engine without a B200 fails loudly (there is no CPU fallback);
+* the planner's instruction streams, executed by the numpy emulator in tests/isa_emu.py,
+  reproduce the oracle: Gram / A^T y entries, EVAL_ONLY residual sums, materialised terms and
+  residual passes, with and without cross-candidate sharing, chunked and tile-constrained.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from rils_rols_b200 import batch as B
+from rils_rols_b200 import engine as E
+from tests import isa_emu as EMU
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rr_b200.h")).read()
+    names = re.findall(r"RR_API\s+[\w\s\*]+?\b(rr_\w+)\s*\(", hdr)
+    assert len(names) >= 15 and set(E.EXPORTS) <= set(names)
+    L = E.lib()
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/rr_b200.h but not exported"
+    assert L.rr_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(E.EngineError) as ei:
+        E.Engine(np.ones((8, 2)), np.ones(8))
+    assert "no CUDA device" in str(ei.value) or "CPU fallback" in str(ei.value)
+
+
+def gram_from_dots(plan, dots, batch, c, n):
+    m = int(batch.cand_term_begin[c + 1] - batch.cand_term_begin[c])
+    idx = plan.tab[plan.tab_begin[c]:plan.tab_begin[c + 1]]
+    assert idx.size == m * (m + 1) // 2 + 2 * m
+    G = np.zeros((m + 1, m + 1))
+    p = 0
+    for i in range(m):
+        for j in range(i, m):
+            G[i, j] = G[j, i] = dots[idx[p]]
+            p += 1
+    byc = np.array([dots[idx[p + i]] for i in range(m)])
+    p += m
+    for i in range(m):
+        G[i, m] = G[m, i] = dots[idx[p + i]]
+    G[m, m] = n
+    return G, byc
+
+
+def design(Xfm, batch, c):
+    cols = []
+    for t in range(int(batch.cand_term_begin[c]), int(batch.cand_term_begin[c + 1])):
+        cols.append(O.evaluate(Xfm, batch.code[batch.term_code_begin[t]:batch.term_code_begin[t + 1]], batch.consts))
+    cols.append(np.ones(Xfm.shape[1]))
+    return np.stack(cols, axis=1)
+
+
+@pytest.mark.parametrize("no_cse,target_chunks,tile_cols", [(False, 1, 56), (True, 1, 56), (False, 7, 56), (False, 1, 12)])
+@pytest.mark.parametrize("cfg,prefix", [("cfg1_toy", "ls3_"), ("cfg3_breast_cancer", "ls0_")])
+def test_gram_plan_reproduces_design_matrix_products(golden, cfg, prefix, no_cse, target_chunks, tile_cols):
+    z = golden(cfg)
+    X, y = z["X"], z["y"]
+    batch = B.Batch.load_fields(z, prefix).subset(range(0, 300))
+    if tile_cols == 12 and X.shape[1] > 4:
+        tile_cols = 20  # each chunk stages only the columns it touches; 30 features do not fit at once
+    plan = EMU.Plan(batch, X.shape[1], EMU.KIND_GRAM, tile_cols=tile_cols, target_chunks=target_chunks, no_cse=no_cse)
+    assert plan.max_tile_cols <= tile_cols
+    if target_chunks > 1:
+        assert len(plan.chunks) > 1
+    G_cols = EMU.engine_columns(X, y)
+    dots, _ = EMU.run(plan, G_cols)
+    Xfm = O.feature_major(X)
+    yc = y - y.mean()
+    with np.errstate(all="ignore"):
+        for c in range(0, batch.n_cand, 7):
+            A = design(Xfm, batch, c)
+            G, byc = gram_from_dots(plan, dots, batch, c, X.shape[0])
+            want = A.T @ A
+            ok = np.isclose(G, want, rtol=1e-12, atol=0, equal_nan=True) | (~np.isfinite(want) & ~np.isfinite(G))
+            assert ok.all(), f"cand {c}"
+            wb = A[:, :-1].T @ yc
+            okb = np.isclose(byc, wb, rtol=1e-10, atol=1e-9 * np.abs(yc).sum(), equal_nan=True) | (~np.isfinite(wb) & ~np.isfinite(byc))
+            assert okb.all(), f"cand {c}"
+    if not no_cse:
+        # sharing: far fewer evaluations than term instances
+        assert plan.n_terms_distinct < batch.n_terms
+        if cfg == "cfg1_toy":
+            assert plan.n_terms_distinct < 0.5 * batch.n_terms and plan.w_issued < plan.w_contract
+
+
+@pytest.mark.parametrize("cfg", ["cfg1_toy", "cfg2_diabetes", "cfg3_breast_cancer"])
+def test_eval_plan_reproduces_fitness(golden, cfg):
+    z = golden(cfg)
+    X, y = z["X"], z["y"]
+    batch = B.Batch.load_fields(z, "pert0_")
+    plan = EMU.Plan(batch, X.shape[1], EMU.KIND_EVAL, target_chunks=5)
+    dots, _ = EMU.run(plan, EMU.engine_columns(X, y))
+    sst = float(((y - y.mean()) ** 2).sum())
+    n_ok = 0
+    for c in range(batch.n_cand):
+        size = int(batch.term_code_begin[c + 1] - batch.term_code_begin[c])
+        f = B.fitness_tuple(dots[plan.tab[c]], sst, X.shape[0], size)
+        ref = (z["pert0_ref_f0"][c], z["pert0_ref_f1"][c], int(z["pert0_ref_size"][c]))
+        assert f[2] == ref[2]
+        if np.isfinite(ref[0]):
+            assert abs(f[0] - ref[0]) <= 1e-12 * max(1, abs(ref[0])) and abs(f[1] - ref[1]) <= 1e-12 * max(1, abs(ref[1]))
+            n_ok += 1
+        else:
+            assert f[0] == ref[0]
+    assert n_ok > 5
+
+
+def test_materialise_plan_is_bit_exact_for_arithmetic_terms(golden):
+    z = golden("cfg2_diabetes")
+    X, y = z["X"], z["y"]
+    batch = B.Batch.load_fields(z, "ls2_").subset(range(200))
+    plan = EMU.Plan(batch, X.shape[1], EMU.KIND_MATERIALISE, target_chunks=3)
+    _, V = EMU.run(plan, EMU.engine_columns(X, y), n_stg=plan.n_terms_distinct)
+    Xfm = O.feature_major(X)
+    transcend = {B.OP_SIN, B.OP_COS, B.OP_LN, B.OP_EXP, B.OP_POW}
+    n_exact = 0
+    for t in range(batch.n_terms):
+        code = batch.code[batch.term_code_begin[t]:batch.term_code_begin[t + 1]]
+        want = O.evaluate(Xfm, code, batch.consts)
+        got = V[plan.term_ids[t]]
+        if set((code & 0xFF).tolist()) & transcend:
+            assert np.allclose(got, want, rtol=1e-14, atol=0, equal_nan=True)
+        else:
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+            n_exact += 1
+    assert n_exact > 50
+
+
+def test_residual_plan_matches_rebuilt_model(golden):
+    z = golden("cfg1_toy")
+    X, y = z["X"], z["y"]
+    batch = B.Batch.load_fields(z, "ls1_").subset(range(120))
+    Xfm = O.feature_major(X)
+    ores, f0, f1, fs = O.score_batch(Xfm, y, batch)
+    cs = ores.coef[: batch.n_coef].copy()
+    cs[np.abs(cs) < 1e-12] = 0.0
+    for c in range(batch.n_cand):  # value_one applies to term coefficients, not to the free term
+        sl = batch.coef_slice(c)
+        seg = cs[sl]
+        seg[:-1][np.abs(seg[:-1] - 1.0) < 1e-12] = 1.0
+    cs[~np.isfinite(cs)] = 0.0
+    plan = EMU.Plan(batch, X.shape[1], EMU.KIND_RESIDUAL, coef=cs)
+    dots, _ = EMU.run(plan, EMU.engine_columns(X, y))
+    n_ok = 0
+    for c in range(batch.n_cand):
+        if not np.all(np.isfinite(ores.coef[batch.coef_slice(c)])) or not np.isfinite(ores.ssr[c]):
+            continue
+        idx = plan.tab[plan.tab_begin[c]:plan.tab_begin[c + 1]]
+        m = int(batch.cand_term_begin[c + 1] - batch.cand_term_begin[c])
+        assert idx.size == m + 2
+        assert abs(dots[idx[0]] - ores.ssr[c]) <= 1e-9 * max(ores.ssr[c], 1e-6), c
+        n_ok += 1
+    assert n_ok > 60
+
+
+def test_planner_rejects_malformed_batches():
+    good = B.Batch.from_exprs(B.MODE_OLS_FIT, [[B.Expr.var(0) * B.Expr.var(1)]])
+    EMU.Plan(good, 2, EMU.KIND_GRAM)
+    with pytest.raises(ValueError):  # feature index out of range
+        EMU.Plan(good, 1, EMU.KIND_GRAM)
+    bad = B.Batch(B.MODE_OLS_FIT, [0, 1], [0, 2], np.array([B.ins(B.OP_VAR, 0), B.ins(B.OP_VAR, 0)], dtype=np.uint32), np.zeros(0))
+    with pytest.raises(ValueError):  # two values left on the stack
+        EMU.Plan(bad, 2, EMU.KIND_GRAM)
+    bad2 = B.Batch(B.MODE_OLS_FIT, [0, 1], [0, 1], np.array([B.ins(B.OP_PLUS)], dtype=np.uint32), np.zeros(0))
+    with pytest.raises(ValueError):  # stack underflow
+        EMU.Plan(bad2, 2, EMU.KIND_GRAM)
+    bad3 = B.Batch(B.MODE_OLS_FIT, [0, 1], [0, 1], np.array([B.ins(B.OP_CONST, 5)], dtype=np.uint32), np.zeros(2))
+    with pytest.raises(ValueError):  # constant index out of range
+        EMU.Plan(bad3, 2, EMU.KIND_GRAM)
+    bad4 = B.Batch(B.MODE_EVAL_ONLY, [0, 2], [0, 1, 2], np.array([B.ins(B.OP_VAR, 0)] * 2, dtype=np.uint32), np.zeros(0))
+    with pytest.raises(ValueError):  # EVAL_ONLY takes one program per candidate
+        EMU.Plan(bad4, 2, EMU.KIND_EVAL)
+
+
+def test_deep_trees_spill_into_slots():
+    """A balanced tree needs spill temporaries (no dynamic stack in the kernel)."""
+    v = B.Expr.var
+
+    def bal(depth, k=0):
+        if depth == 0:
+            return B.sin(v(k % 3)), k + 1
+        l, k = bal(depth - 1, k)
+        r, k = bal(depth - 1, k)
+        return (l * r if depth % 2 else l + r), k
+
+    e, _ = bal(5)
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0.5, 1.5, size=(40, 3))
+    y = rng.normal(size=40)
+    batch = B.Batch.from_exprs(B.MODE_EVAL_ONLY, [[e]])
+    plan = EMU.Plan(batch, 3, EMU.KIND_EVAL)
+    assert (plan.ins["w0"] & 0xFF == EMU.RI_ST).sum() >= 5
+    dots, _ = EMU.run(plan, EMU.engine_columns(X, y))
+    code, consts = e.program()
+    want = float(((y - O.evaluate(O.feature_major(X), code, consts)) ** 2).sum())
+    assert abs(dots[plan.tab[0]] - want) <= 1e-12 * want
