@@ -269,3 +269,21 @@ def test_wide_data_uses_per_chunk_column_staging():
             r = eng.score(batch)
             rep = parity.compare(batch, r, ref, Xfm, y, eng.info().sst, O.evaluate, f"wide flags={flags}", check_nzp=flags == 0)
             assert rep["well_posed"] >= 190
+
+
+def test_sample_sharded_engine_matches_unsharded():
+    """Two ranks (one per GPU) over NCCL: needs >= 2 GPUs, skipped on a single-GPU box. The same
+    check runs standalone: torchrun --nproc-per-node 2 tests/sharded_check.py"""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "sharded_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
