@@ -193,7 +193,7 @@ py::tuple debug_rebuild(UArr code, DArr consts, DArr coef)
 PYBIND11_MODULE(rils_rols_cpp, m)
 {
     m.doc() = "RILS-ROLS driver on the B200 scoring engine (drop-in for the reference's rils_rols_cpp)";
-    py::class_<PyRilsRols>(m, "rils_rols")
+    py::class_<PyRilsRols>(m, "rils_rols", py::module_local())
         .def(py::init<bool, int, int, double, int, double, bool, int>())
         .def("fit", &PyRilsRols::fit)
         .def("predict", &PyRilsRols::predict)

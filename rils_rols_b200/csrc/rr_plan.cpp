@@ -563,11 +563,20 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
             if (room < 2) return "tile too small";
             // t = u; reductions of u with itself, ones, yc and every partner already resident
             auto reduce_term = [&](int32_t u, const std::vector<int32_t> &done) {
+                const bool self = missing(u, u), one = missing(u, KEY_ONE), with_yc = missing(u, KEY_YC);
+                bool any = self || one || with_yc;
+                for (int32_t v : done)
+                    if (v != u && missing(u, v)) { any = true; break; }
+                if (!any) {
+                    // all of u's missing pairs are with terms that come later: they are reduced when
+                    // that term is in t; u only has to be resident by then
+                    ch.ensure(u);
+                    return;
+                }
                 ch.ensure_tos(u);
-                const bool self = missing(u, u), one = missing(u, KEY_ONE);
                 partners.clear();
                 pkeys.clear();
-                if (missing(u, KEY_YC)) { partners.push_back(yc_col); pkeys.push_back(key(u, KEY_YC)); }
+                if (with_yc) { partners.push_back(yc_col); pkeys.push_back(key(u, KEY_YC)); }
                 for (int32_t v : done) {
                     if (v == u || !missing(u, v)) continue;
                     const int32_t sv = ch.lookup(v);

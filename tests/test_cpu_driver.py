@@ -10,9 +10,7 @@ import pytest
 from oracle import pyoracle as O
 from rils_rols_b200 import batch as B
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "rils_rols_b200"))
-import rils_rols_cpp as M  # noqa: E402
+from rils_rols_b200 import rils_rols_cpp as M  # noqa: E402
 
 
 def expr_from_postfix(code, consts) -> B.Expr:
