@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -194,7 +195,8 @@ struct rr_engine {
     int rank = 0, world = 1;
     // grow-only work buffers
     DevBuf d_ins, d_chunks, d_cols, d_acc, d_dots, d_rdots, d_tab, d_rtab, d_ws, d_wsoff, d_list, d_coef, d_cs,
-        d_nzp, d_ssr, d_flags, d_status, d_delta, d_V, d_A, d_rhs, d_aux, d_perm, d_ctb, d_tid, d_misc, d_gather;
+        d_nzp, d_ssr, d_flags, d_status, d_delta, d_V, d_A, d_rhs, d_aux, d_perm, d_ctb, d_tid, d_misc, d_gather,
+        d_t0, d_t1, d_t2, d_t3, d_t4;  // small per-pass tables of the Gram path
     HostBuf h_stage, h_out;
     rr_stats stats{};
     std::string error;
@@ -214,7 +216,7 @@ struct rr_engine {
     {
         for (DevBuf *b : {&X, &d_ins, &d_chunks, &d_cols, &d_acc, &d_dots, &d_rdots, &d_tab, &d_rtab, &d_ws, &d_wsoff,
                           &d_list, &d_coef, &d_cs, &d_nzp, &d_ssr, &d_flags, &d_status, &d_delta, &d_V, &d_A, &d_rhs,
-                          &d_aux, &d_perm, &d_ctb, &d_tid, &d_misc, &d_gather})
+                          &d_aux, &d_perm, &d_ctb, &d_tid, &d_misc, &d_gather, &d_t0, &d_t1, &d_t2, &d_t3, &d_t4})
             b->release();
         h_stage.release();
         h_out.release();
@@ -673,6 +675,17 @@ int run_exact(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *
 // ---- OLS_FIT, Gram path -----------------------------------------------------------------------
 int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *res)
 {
+    const bool verbose = env_int("RR_B200_VERBOSE", 0) != 0;
+    auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tlast = tnow();
+    auto phase = [&](const char *name) {
+        if (!verbose) return;
+        cudaStreamSynchronize(e->stream);
+        const double t = tnow();
+        std::fprintf(stderr, "[rr_b200] %-28s %8.2f ms\n", name, t - tlast);
+        tlast = t;
+    };
+
     const SweepCfg S = choose_cfg(e);
     const int nc = b->n_cand;
     const int n_terms = b->cand_term_begin[nc];
@@ -687,8 +700,10 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     std::vector<int32_t> tab, tab_begin;
     std::string err = bp.plan_gram(lim, cols, nullptr, false, P1, tab, tab_begin);
     if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
+    phase("plan gram");
     rc = run_sweep(e, P1, S, e->d_dots, false, nullptr, 0);
     if (rc) return rc;
+    phase("sweep gram");
 
     // per-candidate solve
     std::vector<int64_t> wsoff(nc + 1, 0);
@@ -723,6 +738,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     CU(cudaGetLastError());
     e->stats.kernel_launches++;
 
+    phase("gram solve launch");
     std::vector<uint32_t> status(nc);
     CU(cudaMemcpyAsync(status.data(), e->d_status.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -760,8 +776,8 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
         rc = run_sweep(e, Pd, S, e->d_rdots, true, nullptr, 0);
         if (rc) return rc;
-        DevBuf d_dt, d_dtb, d_l, d_wo;
-        auto cleanup = [&]() { d_dt.release(); d_dtb.release(); d_l.release(); d_wo.release(); };
+        DevBuf &d_dt = e->d_t0, &d_dtb = e->d_t1, &d_l = e->d_t2, &d_wo = e->d_t3;
+        auto cleanup = [&]() {};
         std::vector<int64_t> wso(escalate.size() + 1, 0);
         for (size_t i = 0; i < escalate.size(); ++i) {
             const int64_t kk = bp.k_of(escalate[i]);
@@ -791,6 +807,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         e->stats.dd += escalate.size();
     }
 
+    phase("solve + dd pass");
     // pass 3: explicit residuals for the refine set (and the SSR of the escalated set)
     std::vector<int32_t> pending(refine);
     bool first_round = true;
@@ -828,8 +845,8 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
                 else { l_esc.push_back(ok[i]); rb_esc.push_back(rtab_begin[i]); }
             }
         }
-        DevBuf d_rt, d_l, d_b, d_wo, d_rb;
-        auto cleanup = [&]() { d_rt.release(); d_l.release(); d_b.release(); d_wo.release(); d_rb.release(); };
+        DevBuf &d_rt = e->d_t0, &d_l = e->d_t1, &d_b = e->d_t2, &d_wo = e->d_t3, &d_rb = e->d_t4;
+        auto cleanup = [&]() {};
         if ((rc = upload(e, d_rt, rtab.data(), rtab.size()))) { cleanup(); return rc; }
         if (!l_esc.empty()) {
             if ((rc = upload(e, d_l, l_esc.data(), l_esc.size())) || (rc = upload(e, d_rb, rb_esc.data(), rb_esc.size()))) { cleanup(); return rc; }
@@ -870,7 +887,10 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         pending.swap(next);
         first_round = false;
     }
-    return download_results(e, b, res, true);
+    phase("residual pass");
+    rc = download_results(e, b, res, true);
+    phase("download");
+    return rc;
 }
 
 }  // namespace

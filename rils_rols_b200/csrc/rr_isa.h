@@ -48,6 +48,8 @@ enum RRInsOp : uint32_t {
     // Reductions over the samples with a = t: aux bit 0 = also t.t, bit 1 = also sum(t),
     // bits 8-15 (of aux) = number of tile-column partners (<= 6, 16-bit column indices packed in
     // w1 and imm). Outputs in that order, ids implicit and consecutive from the chunk's dot_base.
+    // Fused prologue (peephole of the planner): aux bit 2 = first store t to tile column
+    // (w0 >> 24), aux bit 3 = first load t from that column.
     RI_MDOT,
     RI_MDOTDD,  // same, accumulated in double-double (two outputs per reduction: hi, lo)
     // classifier metrics of t against y = tile[w1] (rils_rols_cpp.cpp:51-86): three outputs
@@ -61,6 +63,8 @@ enum : uint32_t {
     RB_SWAP = 1u << 5,   // t = src op t
     MD_SELF = 1u << 0,
     MD_ONE = 1u << 1,
+    MD_ST = 1u << 2,
+    MD_LD = 1u << 3,
     MD_MAX_PARTNERS = 6,
 };
 #define RR_W0(op, aux) ((uint32_t)(op) | ((uint32_t)(aux) << 8))

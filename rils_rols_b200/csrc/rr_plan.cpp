@@ -86,6 +86,7 @@ std::string BatchPlanner::build_term(int32_t code_begin, int32_t code_len, Term 
         if (op == RR_OP_NONE || op >= RR_OP_COUNT) return "bad opcode";
         TermNode n;
         n.op = (uint8_t)op;
+        n.first = i;
         const int ar = arity(op);
         if ((int)st.size() < ar) return "malformed postfix (stack underflow)";
         if (op == RR_OP_CONST) {
@@ -98,6 +99,7 @@ std::string BatchPlanner::build_term(int32_t code_begin, int32_t code_len, Term 
             if (ar == 2) { n.right = st.back(); st.pop_back(); }
             n.left = st.back();
             st.pop_back();
+            n.first = t.nodes[n.left].first;
             const TermNode &L = t.nodes[n.left];
             if (ar == 1) {
                 n.need = L.need;
@@ -158,6 +160,34 @@ std::string BatchPlanner::analyse(bool no_cse)
         terms_.push_back(std::move(tm));
         term_id_[t] = id;
         if (!no_cse) seen.emplace(key, id);
+    }
+    // subtree-level sharing: an inner subtree that is itself one of the batch's distinct terms can be
+    // read from that term's slot when it is resident (neighbours are built by wrapping or combining
+    // existing terms: `t * x3`, `cos(t)`, ...)
+    if (!no_cse) {
+        for (Term &tm : terms_) {
+            const int32_t root = (int32_t)tm.nodes.size() - 1;
+            for (int32_t x = 0; x < root; ++x) {
+                TermNode &nd = tm.nodes[x];
+                if (nd.leaf()) continue;
+                key.clear();
+                for (int32_t i = tm.code_begin + nd.first; i <= tm.code_begin + x; ++i) {
+                    const uint32_t w = b_->code[i];
+                    const uint32_t op = RR_INS_OP(w);
+                    key.push_back((char)op);
+                    if (op == RR_OP_CONST) {
+                        char buf[8];
+                        std::memcpy(buf, &b_->consts[RR_INS_ARG(w)], 8);
+                        key.append(buf, 8);
+                    } else if (op == RR_OP_VAR) {
+                        const uint32_t a = RR_INS_ARG(w);
+                        key.append((const char *)&a, 4);
+                    }
+                }
+                auto it = seen.find(key);
+                if (it != seen.end()) nd.sub_term = it->second;
+            }
+        }
     }
     // contract weights, SURVEY.md 8(d): W(c) = sum w(op) + k(k+1)/2 + k + (k + 2)
     cand_w_.assign(b_->n_cand, 0.0);
@@ -274,12 +304,50 @@ struct BatchPlanner::Chunk {
     }
     void unpin_all() { ++epoch; }
 
+    // a node that can be used as an operand without evaluation: a constant, a staged feature, or an
+    // inner subtree equal to a distinct term that is resident in a slot right now. For the latter the
+    // slot is pinned only until the consuming instruction has been emitted (release()).
+    struct Operand {
+        bool ok = false, konst = false;
+        uint32_t col = 0;
+        double imm = 0.0;
+        int32_t slot = -1;       // >= 0: resident sub-term
+        uint64_t saved_pin = 0;
+    };
+    Operand operand_of(const TermNode &n)
+    {
+        Operand o;
+        if (n.op == RR_OP_CONST) { o.ok = true; o.konst = true; o.imm = n.cval; return o; }
+        if (n.op == RR_OP_VAR) { o.ok = true; o.col = staged(n.var); return o; }
+        if (n.sub_term >= 0) {
+            auto it = term_slot.find(n.sub_term);
+            if (it != term_slot.end()) {
+                o.ok = true;
+                o.slot = it->second;
+                o.col = (uint32_t)o.slot;
+                o.saved_pin = slot_pin[o.slot];
+                slot_pin[o.slot] = epoch;
+                slot_stamp[o.slot] = clock++;
+            }
+        }
+        return o;
+    }
+    void release(const Operand &o)
+    {
+        if (o.slot >= 0) slot_pin[o.slot] = o.saved_pin;
+    }
+
     // leaves t = value(node x)
     void gen(const Term &T, int32_t x)
     {
         const TermNode &n = T.nodes[x];
-        if (n.op == RR_OP_CONST) { emit(RI_LOAD_C, 0, n.cval, 0); return; }
-        if (n.op == RR_OP_VAR) { emit(RI_LOAD_M, staged(n.var), 0.0, 0); return; }
+        Operand o = operand_of(n);
+        if (o.ok) {
+            if (o.konst) emit(RI_LOAD_C, 0, o.imm, 0);
+            else emit(RI_LOAD_M, o.col, 0.0, 0);
+            release(o);
+            return;
+        }
         const int ar = arity(n.op);
         if (ar == 1) {
             gen(T, n.left);
@@ -287,16 +355,18 @@ struct BatchPlanner::Chunk {
             return;
         }
         const TermNode &L = T.nodes[n.left], &R = T.nodes[n.right];
-        auto leaf_operand = [&](const TermNode &lf, bool swap) {
-            if (lf.op == RR_OP_CONST) emit(bin_ins(n.op, true, swap), 0, lf.cval, kW[n.op]);
-            else emit(bin_ins(n.op, false, swap), staged(lf.var), 0.0, kW[n.op]);
-        };
-        if (R.leaf()) {
+        Operand ro = operand_of(R);
+        if (ro.ok) {
             gen(T, n.left);
-            leaf_operand(R, false);
-        } else if (L.leaf()) {
+            emit(bin_ins(n.op, ro.konst, false), ro.col, ro.imm, kW[n.op]);
+            release(ro);
+            return;
+        }
+        Operand lo = operand_of(L);
+        if (lo.ok) {
             gen(T, n.right);
-            leaf_operand(L, true);
+            emit(bin_ins(n.op, lo.konst, true), lo.col, lo.imm, kW[n.op]);
+            release(lo);
         } else if (L.need >= R.need) {
             gen(T, n.left);
             const int32_t s = alloc_slot(-2);
@@ -410,6 +480,27 @@ struct BatchPlanner::Chunk {
             x.w1 = (uint32_t)p[0] | ((uint32_t)p[1] << 16);
             const uint64_t hi = (uint64_t)p[2] | ((uint64_t)p[3] << 16) | ((uint64_t)p[4] << 32) | ((uint64_t)p[5] << 48);
             std::memcpy(&x.imm, &hi, 8);
+        }
+        // peephole: "ST s; MDOT" and "LOAD_M s; MDOT" become one instruction (the tile column rides in
+        // the top byte of w0): one dispatch less for the two most frequent instruction pairs
+        {
+            std::vector<RRIns> out;
+            out.reserve(P.ins.size() - pc_begin);
+            for (size_t i = pc_begin; i < P.ins.size(); ++i) {
+                const RRIns &x = P.ins[i];
+                const uint32_t op = RR_OP(x.w0);
+                if ((op == RI_ST || op == RI_LOAD_M) && i + 1 < P.ins.size() && RR_OP(P.ins[i + 1].w0) == RI_MDOT &&
+                    x.w1 < 256 && !(RR_AUX(P.ins[i + 1].w0) & (MD_ST | MD_LD))) {
+                    RRIns m = P.ins[i + 1];
+                    m.w0 |= ((op == RI_ST ? MD_ST : MD_LD) << 8) | (x.w1 << 24);
+                    out.push_back(m);
+                    ++i;
+                    continue;
+                }
+                out.push_back(x);
+            }
+            P.ins.resize(pc_begin);
+            P.ins.insert(P.ins.end(), out.begin(), out.end());
         }
         RRChunk c;
         std::memset(&c, 0, sizeof(c));
@@ -647,7 +738,8 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
     const int32_t need = max_need(*this, units);
     int32_t widest = 0;
     for (const Unit &u : units) widest = std::max(widest, (int32_t)u.terms.size());
-    const int32_t min_slots = widest + need + 2;
+    // all terms resident when they fit; wide candidates stream their terms instead (below)
+    const int32_t min_slots = std::min(widest + need + 2, std::max(need + 4, lim.tile_cols / 2));
     std::vector<ChunkSpec> specs;
     std::string err = cut_chunks(*this, units, lim, {cols.y}, min_slots, specs);
     if (!err.empty()) return err + " (residual pass)";
@@ -664,6 +756,42 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
             const int32_t m = (int32_t)T.size();
             const double *cf = coef + b_->cand_term_begin[c] + c;
             ch.unpin_all();
+            if (m + need + 2 > ch.pool_cap) {
+                // wide candidate: not all terms fit the tile at once. Stream them: yhat accumulates in one
+                // slot in the reference's association order, then every term is evaluated a second time
+                // against the residual.
+                const int32_t acc = ch.alloc_slot(-2);
+                bool first = true;
+                for (int32_t i = 0; i < m; ++i) {
+                    const double ci = cf[i];
+                    if (ci == 0.0) continue;
+                    ch.gen_term(T[i]);
+                    if (ci != 1.0) ch.emit(RI_MUL_C, 0, ci, 1);
+                    if (!first) ch.emit(RI_ADD_M, (uint32_t)acc, 0.0, 1);  // acc + c_i t_i (commutative)
+                    ch.emit(RI_ST, (uint32_t)acc, 0.0, 0);
+                    first = false;
+                    if (!ch.err.empty()) return ch.err;
+                }
+                if (first) ch.emit(RI_LOAD_C, 0, cf[m], 0);
+                else if (cf[m] != 0.0) ch.emit(RI_ADD_C, 0, cf[m], 1);
+                ch.emit(RI_RSUB_M, y_col, 0.0, 1);  // t = y - yhat
+                ch.emit(RI_ST, (uint32_t)acc, 0.0, 0);
+                ids.clear();
+                ch.mdot(true, true, {}, false, ids);  // r.r, r.1
+                cand_dot.push_back(ids[0]);
+                const int32_t one_id = ids[1];
+                for (int32_t i = 0; i < m; ++i) {
+                    ch.gen_term(T[i]);
+                    ids.clear();
+                    ch.mdot(false, false, {(uint32_t)acc}, false, ids);  // t_i . r
+                    cand_dot.push_back(ids[0]);
+                    if (!ch.err.empty()) return ch.err;
+                }
+                cand_dot.push_back(one_id);
+                cand_dot_begin.push_back((int32_t)cand_dot.size());
+                ch.free_slot(acc);
+                continue;
+            }
             std::vector<int32_t> slot(m);
             for (int32_t i = 0; i < m; ++i) {
                 slot[i] = ch.ensure(T[i]);

@@ -30,6 +30,8 @@ struct TermNode {
     int32_t var = -1;
     double cval = 0.0;
     int32_t need = 0;  // Sethi-Ullman spill need
+    int32_t first = 0;     // postfix index of the first node of this subtree
+    int32_t sub_term = -1; // distinct term whose whole program equals this subtree (subtree-level sharing)
     bool leaf() const { return op == RR_OP_CONST || op == RR_OP_VAR; }
 };
 

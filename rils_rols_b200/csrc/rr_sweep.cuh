@@ -422,6 +422,16 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     for (int s = 0; s < S; ++s) t[s] = __dmul_rn(t[s], t[s]);
                     break;
                 case RI_MDOT: {
+                    if (w0 & ((MD_ST | MD_LD) << 8)) {
+                        const uint32_t fc = tile_sh + ((w0 >> 24) << CSH);
+                        if (w0 & (MD_ST << 8)) {
+#pragma unroll
+                            for (int s = 0; s < S; ++s) sts_f64(fc + s * SSTR, t[s]);
+                        } else {
+#pragma unroll
+                            for (int s = 0; s < S; ++s) t[s] = lds_f64(fc + s * SSTR);
+                        }
+                    }
                     if (w0 & (MD_SELF << 8)) {
                         double v = 0.0;
 #pragma unroll

@@ -92,7 +92,7 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
             while pc < end:
                 w0, w1, imm = int(plan.ins["w0"][pc]), int(plan.ins["w1"][pc]), float(plan.ins["imm"][pc])
                 pc += 1
-                op, aux = w0 & 0xFF, w0 >> 8
+                op, aux = w0 & 0xFF, (w0 >> 8) & 0xFFFF
                 assert w1 < plan.max_tile_cols or op in (RI_STG, RI_MDOT, RI_MDOTDD, RI_END, RI_LOAD_C) or (op % 2 == 1 and RI_ADD_C <= op <= RI_RDIV_C), \
                     f"tile column {w1} out of range"
                 if op == RI_END:
@@ -133,6 +133,10 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     else: t = np.where(x > v, x, v)
                 elif op in (RI_MDOT, RI_MDOTDD):
                     step = 2 if op == RI_MDOTDD else 1
+                    if aux & 4:
+                        tile[w0 >> 24] = t.copy()
+                    elif aux & 8:
+                        t = tile[w0 >> 24].copy()
                     vals = []
                     if aux & 1: vals.append(float(np.dot(t, t)))
                     if aux & 2: vals.append(float(np.sum(t)))

@@ -142,7 +142,8 @@ def test_materialise_plan_is_bit_exact_for_arithmetic_terms(golden):
     assert n_exact > 50
 
 
-def test_residual_plan_matches_rebuilt_model(golden):
+@pytest.mark.parametrize("tile_cols", [56, 10])  # 10: wide candidates stream their terms
+def test_residual_plan_matches_rebuilt_model(golden, tile_cols):
     z = golden("cfg1_toy")
     X, y = z["X"], z["y"]
     batch = B.Batch.load_fields(z, "ls1_").subset(range(120))
@@ -155,7 +156,8 @@ def test_residual_plan_matches_rebuilt_model(golden):
         seg = cs[sl]
         seg[:-1][np.abs(seg[:-1] - 1.0) < 1e-12] = 1.0
     cs[~np.isfinite(cs)] = 0.0
-    plan = EMU.Plan(batch, X.shape[1], EMU.KIND_RESIDUAL, coef=cs)
+    plan = EMU.Plan(batch, X.shape[1], EMU.KIND_RESIDUAL, coef=cs, tile_cols=tile_cols)
+    assert plan.max_tile_cols <= tile_cols
     dots, _ = EMU.run(plan, EMU.engine_columns(X, y))
     n_ok = 0
     for c in range(batch.n_cand):
@@ -165,6 +167,16 @@ def test_residual_plan_matches_rebuilt_model(golden):
         m = int(batch.cand_term_begin[c + 1] - batch.cand_term_begin[c])
         assert idx.size == m + 2
         assert abs(dots[idx[0]] - ores.ssr[c]) <= 1e-9 * max(ores.ssr[c], 1e-6), c
+        # r.t_i and r.1 against the design matrix
+        A = design(Xfm, batch, c)
+        cz = cs[batch.coef_slice(c)]
+        yh = np.zeros(X.shape[0])
+        for j in range(m + 1):
+            yh = yh + cz[j] * A[:, j]
+        r = y - yh
+        want = np.concatenate([A[:, :m].T @ r, [r.sum()]])
+        got = np.array([dots[i] for i in idx[1:]])
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-7 * (np.abs(A).sum(axis=0) * np.abs(r).max()).max()), c
         n_ok += 1
     assert n_ok > 60
 
