@@ -123,8 +123,9 @@ std::string BatchPlanner::analyse(bool no_cse)
 {
     if (!b_ || b_->n_cand < 0) return "null batch";
     if (b_->n_cand == 0) return "";
-    if (!b_->cand_term_begin || !b_->term_code_begin || !b_->code) return "null batch arrays";
+    if (!b_->cand_term_begin || !b_->term_code_begin) return "null batch arrays";
     const int32_t n_terms = b_->cand_term_begin[b_->n_cand];
+    if (n_terms > 0 && !b_->code) return "null batch arrays";  // a batch of term-less candidates has no code
     if (b_->cand_term_begin[0] != 0 || b_->term_code_begin[0] != 0) return "offset arrays must start at 0";
     term_id_.assign(n_terms, -1);
     terms_.clear();

@@ -287,3 +287,16 @@ def test_sample_sharded_engine_matches_unsharded():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "sharded_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_termless_candidates_only():
+    """tune_constants() of a constant tree: no factors at all, only the free term (code pointer may be NULL)."""
+    rng = np.random.default_rng(9)
+    X = rng.uniform(size=(5000, 2))
+    y = 3.0 + 0.1 * rng.normal(size=5000)
+    b = B.Batch(B.MODE_OLS_FIT, [0, 0, 0], [0], np.zeros(0, dtype=np.uint32), np.zeros(0))
+    for flags in (0, B.FLAG_FORCE_GRAM, B.FLAG_FORCE_EXACT):
+        with Engine(X, y, flags=flags) as eng:
+            r = eng.score(b)
+            assert np.allclose(r.coef[:2], y.mean(), rtol=1e-12)
+            assert np.allclose(r.ssr[:2], ((y - y.mean()) ** 2).sum(), rtol=1e-10)
