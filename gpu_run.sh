@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-python tools/fit_configs.py --ref 2>&1 | tail -20 | cut -c1-500
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_r1d.json | cut -c1-200

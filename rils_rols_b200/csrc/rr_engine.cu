@@ -328,8 +328,9 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     const int64_t stride = round_up(std::max(P.n_dots, 1), 32) + 32;
     // keep the accumulator rows within a sane budget
     const size_t row_budget = (size_t)env_double("RR_B200_ACC_BYTES", 6e9);
-    while (gx > 1 && (size_t)gx * NW * stride * 8 > row_budget) gx = (gx + 1) / 2;
-    const int rows = gx * NW;
+    (void)NW;
+    while (gx > 1 && (size_t)gx * stride * 8 > row_budget) gx = (gx + 1) / 2;
+    const int rows = gx;  // one accumulator row per block
 
     // the kernel streams whole windows of kInsWindow instructions: pad the tail with ENDs
     std::vector<RRIns> ins(P.ins);

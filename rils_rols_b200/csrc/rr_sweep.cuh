@@ -33,7 +33,7 @@
 namespace rr {
 
 constexpr int kInsWindow = 256;  // instructions per shared-memory window (4 KB), two windows
-constexpr size_t kSweepStaticSmem = 2 * (kInsWindow + 1) * 16 + 256;  // windows + mbarriers, rounded up
+constexpr size_t kSweepStaticSmem = 2 * (kInsWindow + 1) * 16 + 2 * 2048 + 256;  // windows + combine buffers + mbarriers
 
 struct SweepArgs {
     const double *X;        // engine matrix: columns (features, y, yc) of `ld` doubles
@@ -183,17 +183,20 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     static_assert((1 << LOG2T) == T, "tile height must be a power of two");
     extern __shared__ __align__(128) double rr_tile[];  // [columns][T]
     __shared__ __align__(16) uint4 ibuf[2][kInsWindow + 1];
+    __shared__ __align__(16) double red[2][8][32];  // cross-warp combine of finished reductions
     __shared__ __align__(8) uint64_t mbar_tile;
     __shared__ __align__(8) uint64_t mbar_ins[2];
 
     const RRChunk ch = a.chunks[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *acc_row = a.acc + ((size_t)blockIdx.x * NW + warp) * (size_t)a.acc_stride + ch.dot_base;
+    double *acc_row = a.acc + (size_t)blockIdx.x * (size_t)a.acc_stride + ch.dot_base;  // one row per block
     const uint4 *prog = reinterpret_cast<const uint4 *>(a.ins + ch.pc_begin);
     const int n_win = (ch.n_ins + kInsWindow - 1) / kInsWindow;
     const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4, up2 = lane & 2, up1 = lane & 1;
     const uint32_t out_slot = __brev((uint32_t)lane) >> 27;  // lane L ends up with reduction bitrev5(L)
     const uint32_t tile_sh = smem_u32(rr_tile) + (uint32_t)tid * 8u;  // this thread's row 0 of column 0
+    const uint32_t red_sh = smem_u32(&red[0][warp][out_slot]);
+    const uint32_t not_warp0 = warp != 0;
     constexpr uint32_t CSH = LOG2T + 3;                               // log2(bytes per tile column)
     constexpr uint32_t SSTR = TH * 8u;                                // byte stride between a thread's samples
     const uint32_t scratch = tile_sh + ((uint32_t)scratch_col << CSH);
@@ -252,8 +255,16 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         x_ = bfly(l3, x_, up2, 2);                                                           \
         if (!(c_ & 16u)) { l4 = x_; break; }                                                 \
         x_ = bfly(l4, x_, up1, 1);                                                           \
-        const uint32_t idx_ = (c_ & ~31u) + out_slot;                                        \
-        if ((int32_t)idx_ < ch.n_dots) atomicAdd(acc_row + idx_, x_); /* RED.E.ADD.F64 */    \
+        /* 32 reductions done: combine the block's warps in fixed order, one RED per reduction */ \
+        const uint32_t buf_ = (c_ >> 5) & 1u;                                                \
+        red[buf_][warp][out_slot] = x_;                                                      \
+        __syncthreads();                                                                     \
+        if (warp == 0) {                                                                     \
+            double s_ = red[buf_][0][out_slot];                                              \
+            for (int w_ = 1; w_ < NW; ++w_) s_ += red[buf_][w_][out_slot];                   \
+            const uint32_t idx_ = (c_ & ~31u) + out_slot;                                    \
+            if ((int32_t)idx_ < ch.n_dots) atomicAdd(acc_row + idx_, s_); /* RED.E.ADD.F64 */ \
+        }                                                                                    \
     } while (0)
 
         bool running = true;
@@ -280,15 +291,15 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                         uint32_t w0, w1;
                         double imm;
                         uint32_t code;
-                        if constexpr (S == 1)
-                            code = rr_core_s1<SSTR, CSH>(t0, t1, t2, t3, l0, l1, l2, l3, l4, cnt, ibp, w0, w1, imm, ib_end,
-                                                         tile_sh, acc_row, ch.n_dots, out_slot, (uint32_t)lane);
-                        else if constexpr (S == 2)
-                            code = rr_core_s2<SSTR, CSH>(t0, t1, t2, t3, l0, l1, l2, l3, l4, cnt, ibp, w0, w1, imm, ib_end,
-                                                         tile_sh, acc_row, ch.n_dots, out_slot, (uint32_t)lane);
-                        else
-                            code = rr_core_s4<SSTR, CSH>(t0, t1, t2, t3, l0, l1, l2, l3, l4, cnt, ibp, w0, w1, imm, ib_end,
-                                                         tile_sh, acc_row, ch.n_dots, out_slot, (uint32_t)lane);
+#define RR_CORE_ARGS t0, t1, t2, t3, l0, l1, l2, l3, l4, cnt, ibp, w0, w1, imm, ib_end, tile_sh, acc_row, ch.n_dots, \
+                     out_slot, (uint32_t)lane, red_sh, not_warp0
+                        if constexpr (S == 1 && NW == 4) code = rr_core_s1_w4<SSTR, CSH>(RR_CORE_ARGS);
+                        else if constexpr (S == 2 && NW == 4) code = rr_core_s2_w4<SSTR, CSH>(RR_CORE_ARGS);
+                        else if constexpr (S == 4 && NW == 4) code = rr_core_s4_w4<SSTR, CSH>(RR_CORE_ARGS);
+                        else if constexpr (S == 1) code = rr_core_s1_w8<SSTR, CSH>(RR_CORE_ARGS);
+                        else if constexpr (S == 2) code = rr_core_s2_w8<SSTR, CSH>(RR_CORE_ARGS);
+                        else code = rr_core_s4_w8<SSTR, CSH>(RR_CORE_ARGS);
+#undef RR_CORE_ARGS
                         if (code == 0) break;
                         if (code == 1) { running = false; break; }
                         const uint32_t col = tile_sh + (w1 << CSH);
@@ -492,13 +503,20 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                             const double l2_ = __shfl_xor_sync(0xffffffffu, lo, m);
                             dd_add(hi, lo, h2, l2_);
                         }
+                        // block combine in double-double (fixed warp order), one writer per (hi, lo) pair
                         if (lane == 0) {
+                            red[0][warp][0] = hi;
+                            red[0][warp][1] = lo;
+                        }
+                        __syncthreads();
+                        if (tid == 0) {
                             double *q = acc_row + 2u * ddcnt;
                             double ah = q[0], al = q[1];
-                            dd_add(ah, al, hi, lo);
+                            for (int w_ = 0; w_ < NW; ++w_) dd_add(ah, al, red[0][w_][0], red[0][w_][1]);
                             q[0] = ah;
                             q[1] = al;
                         }
+                        __syncthreads();
                         ++ddcnt;
                     }
                     break;
