@@ -36,6 +36,15 @@ METRIC = "candidate_fit_evals_per_sec"
 UNIT = "tree-samples/s"
 
 
+def load_traffic():
+    """dram bytes per launch of the dominant kernel, from the committed ncu --set full capture"""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("traffic")
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -290,7 +299,7 @@ def main():
                 "bound": "fp64", "kernel": "rr_sweep_kernel", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12,
                 "unit": "T fp64-pipe thread-instr/s", "frac": achieved / fp64_peak,
                 "peak_source": "measured live: DFMA-only microkernel on this GPU (rr_measure_fp64_peak)",
-                "traffic": None,
+                "traffic": load_traffic() if int(info.n) == (1 << 24) else None,
                 "w_contract_per_sample": w_contract, "w_issued_per_sample": w_shared,
                 "contract_rate_frac": (w_contract * n_local / sweep_s) / fp64_peak,
                 "sweep_ms_per_step": sweep_ms / args.steps,
