@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:rr_sweep -c 1 -o gpurun_out/prof_final_fulln python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+python tools/fit_configs.py --ref > gpurun_out/fit_configs_r1.jsonl 2> gpurun_out/fit_configs_err.log
+tail -3 gpurun_out/fit_configs_err.log
+cat gpurun_out/fit_configs_r1.jsonl | cut -c1-600
