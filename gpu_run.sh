@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-python tools/fit_configs.py --ref > gpurun_out/fit_configs_r1.jsonl 2> gpurun_out/fit_configs_err.log
-tail -3 gpurun_out/fit_configs_err.log
-cat gpurun_out/fit_configs_r1.jsonl | cut -c1-600
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v6.json 2> gpurun_out/bench_v6.err; tail -3 gpurun_out/bench_v6.err; cat gpurun_out/bench_v6.json | cut -c1-1500

@@ -240,7 +240,7 @@ typedef struct rr_debug_plan {
     char error[256];
 } rr_debug_plan;
 RR_API int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kind, int32_t tile_cols,
-                               int32_t max_slots, int32_t target_chunks, int32_t no_cse,
+                               int32_t max_slots, int32_t target_chunks, int32_t no_cse, int32_t n_pins,
                                const double *coef_snapped, rr_debug_plan *out);
 RR_API void rr_debug_plan_free(rr_debug_plan *p);
 

@@ -242,24 +242,25 @@ struct SweepCfg {
     size_t dyn_smem_budget() const
     {
         const size_t per_block = std::min(kSmemPerBlockMax, kSmemPerSM / (size_t)occ - kSmemReserved);
-        return per_block - rr::kSweepStaticSmem;
+        return per_block - rr::sweep_fixed_smem(TH / 32);
     }
-    // columns the planner may use; one more is kept for the kernel's scratch column
-    int tile_cols() const { return (int)std::min<size_t>(dyn_smem_budget() / ((size_t)T() * 8), 0x7000) - 1; }
+    // columns the planner may use
+    int tile_cols() const { return (int)std::min<size_t>(dyn_smem_budget() / ((size_t)T() * 8), 0x3000); }
 };
 
 SweepCfg choose_cfg(const rr_engine *e)
 {
     SweepCfg c;
-    // measured on B200 (profiles/r1_config_sweep.txt): 2 samples per thread in 128-thread blocks,
-    // 3 blocks per SM, is the best trade between per-dispatch overhead (wants more samples per
-    // thread) and latency hiding (wants more warps) under the shared-memory cap on samples in flight
+    // 4 samples per thread (the PTX core of rr_sweep_core.cuh) in 128-thread blocks, 2 blocks per SM:
+    // per-dispatch overhead wants more samples per thread, latency hiding wants more warps, and the
+    // shared-memory tile caps the samples in flight per SM (profiles/r1_config_sweep.txt, r2_*)
     const bool big = e->n >= (1 << 15);
-    c.S = e->s_pref ? e->s_pref : (big ? 2 : 1);
+    c.S = e->s_pref ? e->s_pref : (big ? 4 : 1);
     c.TH = e->th_pref ? e->th_pref : 128;
     c.occ = e->occ_pref ? e->occ_pref : (c.T() >= 1024 ? 1 : (c.T() >= 512 ? 2 : (c.T() >= 256 ? 3 : 4)));
-    // the tile must stage the feature columns a chunk can touch plus a handful of value slots
-    const int want = std::min(e->d, 24) + 1 + 6;
+    // the tile must stage the feature columns a chunk can touch plus a few value slots (cached terms
+    // live in pins first)
+    const int want = std::min(e->d, 24) + 3;
     while (c.tile_cols() < want && c.occ > 1) --c.occ;
     while (c.tile_cols() < want && c.S > 1) c.S /= 2;
     return c;
@@ -274,15 +275,14 @@ template <typename T> int upload(rr_engine *e, DevBuf &buf, const T *src, size_t
     return RR_OK;
 }
 
-using SweepKernel = void (*)(const rr::SweepArgs, const int);
+using SweepKernel = void (*)(const rr::SweepArgs);
 template <bool SP> SweepKernel sweep_kernel_sel(const SweepCfg &c)
 {
     if (c.TH == 128) {
         switch (c.S) {
         case 1: return rr::rr_sweep_kernel<1, 128, SP>;
         case 2: return rr::rr_sweep_kernel<2, 128, SP>;
-        case 4: return rr::rr_sweep_kernel<4, 128, SP>;
-        default: return rr::rr_sweep_kernel<8, 128, SP>;
+        default: return rr::rr_sweep_kernel<4, 128, SP>;
         }
     }
     switch (c.S) {
@@ -315,22 +315,20 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     const int T = cfg.T();
     const int NW = cfg.TH / 32;
     const int n_tiles = (int)((e->n + T - 1) / T);
-    // one extra column: the per-thread scratch the out-of-line operators work on
-    const size_t smem = (size_t)(P.max_tile_cols + 1) * T * 8;
-    if (smem > cfg.dyn_smem_budget()) return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
+    const size_t smem = (size_t)std::max(P.max_tile_cols, 1) * T * 8 + rr::sweep_ring_smem(NW);
+    if (smem > cfg.dyn_smem_budget() + rr::sweep_ring_smem(NW)) return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
     bool special = dd;
     for (const RRIns &x : P.ins)
         if (RR_OP(x.w0) == RI_CLSMET) { special = true; break; }
     SweepKernel kern = sweep_kernel_for(cfg, special);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemPerBlockMax - rr::kSweepStaticSmem)));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemPerBlockMax - rr::sweep_static_smem())));
     const int n_chunks = (int)P.chunks.size();
     int gx = sweep_gx(e, cfg, special, smem, n_chunks, std::max(1, n_tiles));
     const int64_t stride = round_up(std::max(P.n_dots, 1), 32) + 32;
     // keep the accumulator rows within a sane budget
     const size_t row_budget = (size_t)env_double("RR_B200_ACC_BYTES", 6e9);
-    (void)NW;
-    while (gx > 1 && (size_t)gx * stride * 8 > row_budget) gx = (gx + 1) / 2;
-    const int rows = gx;  // one accumulator row per block
+    while (gx > 1 && (size_t)gx * NW * stride * 8 > row_budget) gx = (gx + 1) / 2;
+    const int rows = gx * NW;  // one accumulator row per warp
 
     // the kernel streams whole windows of kInsWindow instructions: pad the tail with ENDs
     std::vector<RRIns> ins(P.ins);
@@ -361,7 +359,7 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     a.ld_stg = ld_stg;
     a.n_tiles = n_tiles;
     CU(cudaEventRecord(e->ev[2], e->stream));
-    kern<<<dim3(gx, n_chunks), cfg.TH, smem, e->stream>>>(a, P.max_tile_cols);
+    kern<<<dim3(gx, n_chunks), cfg.TH, smem, e->stream>>>(a);
     CU(cudaGetLastError());
     CU(cudaEventRecord(e->ev[3], e->stream));
     e->stats.sweep_launches++;

@@ -15,7 +15,8 @@
 //
 // Opcodes are dense (one jump table in the kernel) and specialised by operand kind
 // (_C immediate, _M tile column) and operand order (R* = reversed: t = src op t), so a
-// dispatched case does no further flag tests.
+// dispatched case does no further flag tests. All tile-column forms sit at the top of the
+// opcode range: the dispatcher starts their operand load before it branches.
 #ifndef RR_ISA_H
 #define RR_ISA_H
 
@@ -23,37 +24,49 @@
 
 struct RRIns {
     uint32_t w0;  // opcode | aux << 8
-    uint32_t w1;  // tile column index (operand / destination) or packed MDOT partners
-    double imm;   // constant operand / AXPY coefficient / packed MDOT partners
+    uint32_t w1;  // tile column index (operand / destination); 0 when unused
+    double imm;   // constant operand / AXPY coefficient / packed MDOTDD partners
 };
 static_assert(sizeof(RRIns) == 16, "RRIns must be 16 bytes");
 
+// Besides tile columns the machine has RR_NPIN *pinned value registers* per sample ("pins"): the
+// planner keeps the terms that are reduction partners of many others there (for a local-search
+// neighbourhood: the base solution's terms and the centred target), so that the reductions of a
+// freshly evaluated term against them read no shared memory at all.
+#define RR_NPIN 8
+
 enum RRInsOp : uint32_t {
     RI_END = 0,
+    RI_WINEND,  // never planned: the kernel's sentinel behind each instruction window
     RI_LOAD_C,  // t = imm
-    RI_LOAD_M,  // t = tile[w1]
     RI_ST,      // tile[w1] = t
     RI_STG,     // out[w1][sample] = t   (materialise a column in global memory)
-    RI_ADD_C, RI_ADD_M,    // t = t + src
-    RI_SUB_C, RI_SUB_M,    // t = t - src
-    RI_RSUB_C, RI_RSUB_M,  // t = src - t
-    RI_MUL_C, RI_MUL_M,    // t = t * src
-    RI_DIV_C, RI_DIV_M,    // t = t / src
-    RI_RDIV_C, RI_RDIV_M,  // t = src / t
-    RI_AXPY,    // t = t + imm * tile[w1]  (product rounded, then sum: the c*term + ... chain of
-                //                          rils_rols_cpp.cpp:503-510)
+    RI_LDG,     // t = X[w1][sample]     (engine column straight from global memory, not staged)
+    RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C, RI_RDIV_C,  // t = t op imm / imm op t (R*)
     RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR,  // t = f(t)
     // rarely generated operators share one case: aux = RRRareOp | RB_CONST | RB_SWAP
     RI_RARE,
-    // Reductions over the samples with a = t: aux bit 0 = also t.t, bit 1 = also sum(t),
-    // bits 8-15 (of aux) = number of tile-column partners (<= 6, 16-bit column indices packed in
-    // w1 and imm). Outputs in that order, ids implicit and consecutive from the chunk's dot_base.
-    // Fused prologue (peephole of the planner): aux bit 2 = first store t to tile column
-    // (w0 >> 24), aux bit 3 = first load t from that column.
+    // Reductions over the samples with a = t: aux bit 0 = t.t, bit 1 = sum(t), aux bits 8-15 = mask
+    // of pins to reduce against. Outputs in that order (pins ascending), ids implicit and
+    // consecutive from the chunk's dot_base; at most RR_MDOT_MAX_OUT outputs per instruction.
     RI_MDOT,
-    RI_MDOTDD,  // same, accumulated in double-double (two outputs per reduction: hi, lo)
+    // double-double reductions (escalation plans): aux bit 0/1 as above, aux bits 8-15 = number of
+    // tile-column partners (<= 6, 16-bit column indices packed in w1 and imm); two ids per output
+    RI_MDOTDD,
     // classifier metrics of t against y = tile[w1] (rils_rols_cpp.cpp:51-86): three outputs
     RI_CLSMET,
+    // pins: PIN j: pin[j] = t;  LDP j: t = pin[j];  USEP j: the NEXT instruction (a tile-column
+    // operand form) takes pin[j] as its operand instead of the tile column
+    RI_PIN0,
+    RI_LDP0 = RI_PIN0 + RR_NPIN,
+    RI_USEP0 = RI_LDP0 + RR_NPIN,
+    // ---- forms with a tile-column operand tile[w1]: everything from RI_FIRST_M on ----
+    RI_FIRST_M = RI_USEP0 + RR_NPIN,
+    RI_LOAD_M = RI_FIRST_M,  // t = tile[w1]
+    RI_ADD_M, RI_SUB_M, RI_RSUB_M, RI_MUL_M, RI_DIV_M, RI_RDIV_M,  // t = t op tile[w1] / tile[w1] op t (R*)
+    RI_AXPY,    // t = t + imm * tile[w1]  (product rounded, then sum: the c*term + ... chain of
+                //                          rils_rols_cpp.cpp:503-510)
+    RI_DOTM,    // one reduction: t . tile[w1]
     RI_OPCOUNT
 };
 
@@ -63,14 +76,13 @@ enum : uint32_t {
     RB_SWAP = 1u << 5,   // t = src op t
     MD_SELF = 1u << 0,
     MD_ONE = 1u << 1,
-    MD_ST = 1u << 2,
-    MD_LD = 1u << 3,
-    MD_MAX_PARTNERS = 6,
+    MD_MAX_PARTNERS = 6,  // MDOTDD tile-column partners per instruction
+    RR_MDOT_MAX_OUT = 8,  // outputs of one RI_MDOT (the kernel's reduction ring drains in groups of 8)
 };
 #define RR_W0(op, aux) ((uint32_t)(op) | ((uint32_t)(aux) << 8))
 #define RR_OP(w0) ((w0) & 0xffu)
 #define RR_AUX(w0) ((w0) >> 8)
-#define RR_MDOT_COUNT(w0) (((w0) >> 16) & 0xffu)
+#define RR_MDOT_COUNT(w0) (((w0) >> 16) & 0xffu)  /* MDOTDD partner count / MDOT pin mask */
 
 // One independently schedulable piece of a sweep: its own staged columns, slot state and
 // dot range. Large-n sweeps use one chunk (maximal sharing); small-n sweeps are cut into

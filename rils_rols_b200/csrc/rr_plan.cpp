@@ -33,12 +33,11 @@ int arity(uint32_t op)  // == get_arity, /root/reference/rils_rols_cpp/node.h:40
 // binary node -> specialised opcode for operand kind (konst) and order (swap: t = src op t)
 uint32_t bin_ins(uint32_t op, bool konst, bool swap)
 {
-    const uint32_t k = konst ? 0u : 1u;  // _C opcodes precede their _M twins
     switch (op) {
-    case RR_OP_PLUS: return RR_W0(RI_ADD_C + k, 0);
-    case RR_OP_MULTIPLY: return RR_W0(RI_MUL_C + k, 0);
-    case RR_OP_MINUS: return RR_W0((swap ? RI_RSUB_C : RI_SUB_C) + k, 0);
-    case RR_OP_DIVIDE: return RR_W0((swap ? RI_RDIV_C : RI_DIV_C) + k, 0);
+    case RR_OP_PLUS: return RR_W0(konst ? RI_ADD_C : RI_ADD_M, 0);
+    case RR_OP_MULTIPLY: return RR_W0(konst ? RI_MUL_C : RI_MUL_M, 0);
+    case RR_OP_MINUS: return RR_W0(swap ? (konst ? RI_RSUB_C : RI_RSUB_M) : (konst ? RI_SUB_C : RI_SUB_M), 0);
+    case RR_OP_DIVIDE: return RR_W0(swap ? (konst ? RI_RDIV_C : RI_RDIV_M) : (konst ? RI_DIV_C : RI_DIV_M), 0);
     }
     uint32_t rare = 0;
     switch (op) {
@@ -51,6 +50,10 @@ uint32_t bin_ins(uint32_t op, bool konst, bool swap)
     case RR_OP_MAX: rare = RR_MAX; break;
     }
     return RR_W0(RI_RARE, rare | (konst ? RB_CONST : 0u) | (swap ? RB_SWAP : 0u));
+}
+bool is_rare(uint32_t op)
+{
+    return !(op == RR_OP_PLUS || op == RR_OP_MULTIPLY || op == RR_OP_MINUS || op == RR_OP_DIVIDE);
 }
 
 uint32_t un_ins(uint32_t op)
@@ -66,7 +69,10 @@ uint32_t un_ins(uint32_t op)
     return RI_END;
 }
 
-constexpr uint32_t STAGED = 0x8000u;  // pre-patch marker: operand is a staged column, not a slot
+// pre-patch value locations: a tile slot index, a staged column (STAGED | index) or a pin (PINREF | j)
+constexpr uint32_t STAGED = 0x8000u;
+constexpr uint32_t PINREF = 0x4000u;
+constexpr int32_t PIN_RESERVED = -3;  // pin owner: held for the whole chunk (the centred target)
 
 }  // namespace
 
@@ -222,17 +228,21 @@ struct BatchPlanner::Chunk {
     const PlanLimits &lim;
     int32_t pc_begin, dot_base, col_begin;
     std::unordered_map<int32_t, int32_t> colmap;  // global column -> staged index
-    int32_t pool_cap = 0;                          // slots available in this chunk
+    int32_t pool_cap = 0;                          // tile slots available in this chunk
     std::vector<int32_t> slot_term;                // slot -> cached term (-1 free, -2 temp)
     std::vector<uint64_t> slot_stamp;
     std::vector<uint64_t> slot_pin;
-    std::unordered_map<int32_t, int32_t> term_slot;
-    std::vector<std::vector<uint32_t>> mdot_refs;  // pre-patch partner refs of each MDOT
+    // pins (rr_isa.h): cached terms live there first, tile slots take the overflow and the temporaries
+    int32_t n_pins = 0;
+    int32_t pin_term[RR_NPIN];
+    uint64_t pin_stamp[RR_NPIN], pin_hold[RR_NPIN];
+    std::unordered_map<int32_t, uint32_t> term_loc;  // resident term -> slot index or PINREF | j
+    std::vector<std::vector<uint32_t>> mdot_refs;  // pre-patch partner refs of each MDOTDD
     std::vector<size_t> mdot_at;                   // ... and its instruction index
     uint64_t clock = 1, epoch = 1;
     std::string err;
 
-    Chunk(const BatchPlanner &bp_, SweepPlan &P_, const PlanLimits &lim_, const std::vector<int32_t> &cols)
+    Chunk(const BatchPlanner &bp_, SweepPlan &P_, const PlanLimits &lim_, const std::vector<int32_t> &cols, int32_t pins)
         : bp(bp_), P(P_), lim(lim_)
     {
         pc_begin = (int32_t)P.ins.size();
@@ -243,6 +253,11 @@ struct BatchPlanner::Chunk {
             P.cols.push_back(g);
         }
         pool_cap = std::min(lim.tile_cols - (int32_t)cols.size(), lim.max_slots);
+        n_pins = std::min<int32_t>(std::max(pins, 0), RR_NPIN);
+        for (int j = 0; j < RR_NPIN; ++j) {
+            pin_term[j] = -1;
+            pin_stamp[j] = pin_hold[j] = 0;
+        }
     }
 
     uint32_t staged(int32_t gcol)
@@ -262,7 +277,24 @@ struct BatchPlanner::Chunk {
         P.w_issued += w;
     }
 
-    // a free slot, growing the pool or evicting the least recently used unpinned cached term
+    // pin 0 <- engine column gcol (read from global memory, not staged), held until the chunk ends
+    uint32_t reserve_pin_global(int32_t gcol)
+    {
+        if (n_pins < 1) { err = "internal: no pin to reserve"; return PINREF; }
+        emit(RI_LDG, (uint32_t)gcol, 0.0, 0);
+        emit(RI_PIN0, 0, 0.0, 0);
+        pin_term[0] = PIN_RESERVED;
+        return PINREF | 0u;
+    }
+    int32_t free_pins() const
+    {
+        int32_t f = 0;
+        for (int j = 0; j < n_pins; ++j)
+            if (pin_term[j] != PIN_RESERVED) ++f;
+        return f;
+    }
+
+    // a free tile slot, growing the pool or evicting the least recently used unpinned cached term
     int32_t alloc_slot(int32_t owner)
     {
         int32_t s = -1;
@@ -282,60 +314,125 @@ struct BatchPlanner::Chunk {
                     s = (int32_t)i;
                 }
             if (s < 0) { err = "tile slots exhausted"; return 0; }
-            term_slot.erase(slot_term[s]);
+            term_loc.erase(slot_term[s]);
         }
         slot_term[s] = owner;
         slot_stamp[s] = clock++;
         slot_pin[s] = epoch;
-        if (owner >= 0) term_slot[owner] = s;
+        if (owner >= 0) term_loc[owner] = (uint32_t)s;
         return s;
     }
     void free_slot(int32_t s)
     {
-        if (slot_term[s] >= 0) term_slot.erase(slot_term[s]);
+        if (slot_term[s] >= 0) term_loc.erase(slot_term[s]);
         slot_term[s] = -1;
     }
-    int32_t lookup(int32_t term)
+    // a home for cached term `owner`: a free pin, else the least recently used pin that the current
+    // unit does not hold, else a tile slot
+    uint32_t alloc_loc(int32_t owner)
     {
-        auto it = term_slot.find(term);
-        if (it == term_slot.end()) return -1;
-        slot_stamp[it->second] = clock++;
-        slot_pin[it->second] = epoch;
-        return it->second;
+        int j = -1;
+        for (int i = 0; i < n_pins; ++i)
+            if (pin_term[i] == -1) { j = i; break; }
+        if (j < 0) {
+            uint64_t best = ~0ull;
+            for (int i = 0; i < n_pins; ++i)
+                if (pin_term[i] >= 0 && pin_hold[i] != epoch && pin_stamp[i] < best) {
+                    best = pin_stamp[i];
+                    j = i;
+                }
+            if (j >= 0) term_loc.erase(pin_term[j]);
+        }
+        if (j >= 0) {
+            pin_term[j] = owner;
+            pin_stamp[j] = clock++;
+            pin_hold[j] = epoch;
+            term_loc[owner] = PINREF | (uint32_t)j;
+            return PINREF | (uint32_t)j;
+        }
+        return (uint32_t)alloc_slot(owner);
     }
+    void touch(uint32_t loc)
+    {
+        if (loc & PINREF) {
+            pin_stamp[loc & 0xff] = clock++;
+            pin_hold[loc & 0xff] = epoch;
+        } else {
+            slot_stamp[loc] = clock++;
+            slot_pin[loc] = epoch;
+        }
+    }
+    // location of a resident term or -1
+    int64_t lookup(int32_t term)
+    {
+        auto it = term_loc.find(term);
+        if (it == term_loc.end()) return -1;
+        touch(it->second);
+        return (int64_t)it->second;
+    }
+    bool resident(int32_t term) const { return term_loc.find(term) != term_loc.end(); }
     void unpin_all() { ++epoch; }
 
+    void emit_store(uint32_t loc)
+    {
+        if (loc & PINREF) emit(RI_PIN0 + (loc & 0xff), 0, 0.0, 0);
+        else emit(RI_ST, loc, 0.0, 0);
+    }
+    void emit_load(uint32_t loc)
+    {
+        if (loc & PINREF) emit(RI_LDP0 + (loc & 0xff), 0, 0.0, 0);
+        else emit(RI_LOAD_M, loc, 0.0, 0);
+    }
+    // a tile-column operand form whose operand may sit in a pin: USEP j redirects the operand
+    void emit_m(uint32_t w0, uint32_t loc, double imm, double w)
+    {
+        if (loc & PINREF) {
+            emit(RI_USEP0 + (loc & 0xff), 0, 0.0, 0);
+            emit(w0, 0, imm, w);
+        } else {
+            emit(w0, loc, imm, w);
+        }
+    }
+
     // a node that can be used as an operand without evaluation: a constant, a staged feature, or an
-    // inner subtree equal to a distinct term that is resident in a slot right now. For the latter the
-    // slot is pinned only until the consuming instruction has been emitted (release()).
+    // inner subtree equal to a distinct term that is resident right now. For the latter the
+    // location is held only until the consuming instruction has been emitted (release()).
     struct Operand {
         bool ok = false, konst = false;
         uint32_t col = 0;
         double imm = 0.0;
-        int32_t slot = -1;       // >= 0: resident sub-term
-        uint64_t saved_pin = 0;
+        bool held = false;       // resident sub-term
+        uint64_t saved_hold = 0;
     };
-    Operand operand_of(const TermNode &n)
+    Operand operand_of(const TermNode &n, bool allow_pin = true)
     {
         Operand o;
         if (n.op == RR_OP_CONST) { o.ok = true; o.konst = true; o.imm = n.cval; return o; }
         if (n.op == RR_OP_VAR) { o.ok = true; o.col = staged(n.var); return o; }
         if (n.sub_term >= 0) {
-            auto it = term_slot.find(n.sub_term);
-            if (it != term_slot.end()) {
+            auto it = term_loc.find(n.sub_term);
+            if (it != term_loc.end() && (allow_pin || !(it->second & PINREF))) {
                 o.ok = true;
-                o.slot = it->second;
-                o.col = (uint32_t)o.slot;
-                o.saved_pin = slot_pin[o.slot];
-                slot_pin[o.slot] = epoch;
-                slot_stamp[o.slot] = clock++;
+                o.held = true;
+                o.col = it->second;
+                if (o.col & PINREF) {
+                    o.saved_hold = pin_hold[o.col & 0xff];
+                    pin_hold[o.col & 0xff] = epoch;
+                    pin_stamp[o.col & 0xff] = clock++;
+                } else {
+                    o.saved_hold = slot_pin[o.col];
+                    slot_pin[o.col] = epoch;
+                    slot_stamp[o.col] = clock++;
+                }
             }
         }
         return o;
     }
     void release(const Operand &o)
     {
-        if (o.slot >= 0) slot_pin[o.slot] = o.saved_pin;
+        if (!o.held) return;
+        if (o.col & PINREF) pin_hold[o.col & 0xff] = o.saved_hold;
+        else slot_pin[o.col] = o.saved_hold;
     }
 
     // leaves t = value(node x)
@@ -345,7 +442,7 @@ struct BatchPlanner::Chunk {
         Operand o = operand_of(n);
         if (o.ok) {
             if (o.konst) emit(RI_LOAD_C, 0, o.imm, 0);
-            else emit(RI_LOAD_M, o.col, 0.0, 0);
+            else emit_load(o.col);
             release(o);
             return;
         }
@@ -356,17 +453,20 @@ struct BatchPlanner::Chunk {
             return;
         }
         const TermNode &L = T.nodes[n.left], &R = T.nodes[n.right];
-        Operand ro = operand_of(R);
+        const bool pin_ok = !is_rare(n.op);  // RI_RARE reads its operand from the tile only
+        Operand ro = operand_of(R, pin_ok);
         if (ro.ok) {
             gen(T, n.left);
-            emit(bin_ins(n.op, ro.konst, false), ro.col, ro.imm, kW[n.op]);
+            if (ro.konst) emit(bin_ins(n.op, true, false), 0, ro.imm, kW[n.op]);
+            else emit_m(bin_ins(n.op, false, false), ro.col, 0.0, kW[n.op]);
             release(ro);
             return;
         }
-        Operand lo = operand_of(L);
+        Operand lo = operand_of(L, pin_ok);
         if (lo.ok) {
             gen(T, n.right);
-            emit(bin_ins(n.op, lo.konst, true), lo.col, lo.imm, kW[n.op]);
+            if (lo.konst) emit(bin_ins(n.op, true, true), 0, lo.imm, kW[n.op]);
+            else emit_m(bin_ins(n.op, false, true), lo.col, 0.0, kW[n.op]);
             release(lo);
         } else if (L.need >= R.need) {
             gen(T, n.left);
@@ -392,57 +492,103 @@ struct BatchPlanner::Chunk {
         P.n_term_evals++;
     }
 
-    // make term u resident in a slot AND leave its value in t; returns the slot
-    int32_t ensure_tos(int32_t u)
+    // make term u resident AND leave its value in t; returns its location
+    uint32_t ensure_tos(int32_t u)
     {
-        int32_t s = lookup(u);
+        int64_t s = lookup(u);
         if (s >= 0) {
-            emit(RI_LOAD_M, (uint32_t)s, 0.0, 0);
-            return s;
+            emit_load((uint32_t)s);
+            return (uint32_t)s;
         }
         gen_term(u);
-        s = alloc_slot(u);
-        emit(RI_ST, (uint32_t)s, 0.0, 0);
-        return s;
+        const uint32_t loc = alloc_loc(u);
+        emit_store(loc);
+        return loc;
     }
     // make term u resident (t is clobbered when it has to be evaluated)
-    int32_t ensure(int32_t u)
+    uint32_t ensure(int32_t u)
     {
-        int32_t s = lookup(u);
-        if (s >= 0) return s;
+        int64_t s = lookup(u);
+        if (s >= 0) return (uint32_t)s;
         gen_term(u);
-        s = alloc_slot(u);
-        emit(RI_ST, (uint32_t)s, 0.0, 0);
-        return s;
+        const uint32_t loc = alloc_loc(u);
+        emit_store(loc);
+        return loc;
     }
 
-    // Reductions of t against itself / ones / tile columns (pre-patch column refs). Appends the
-    // output ids in the order self, one, partners...; dd outputs take two ids each.
+    // Reductions of t against itself / ones / value locations (pre-patch refs: pins, tile slots,
+    // staged columns). Appends the output ids in the order self, one, partners... (the caller's
+    // partner order); dd outputs take two ids each and accept tile columns only.
     void mdot(bool self, bool one, const std::vector<uint32_t> &partners, bool dd, std::vector<int32_t> &ids)
     {
-        const int step = dd ? 2 : 1;
-        size_t done = 0;
-        bool first = true;
-        do {
-            const size_t take = std::min<size_t>(MD_MAX_PARTNERS, partners.size() - done);
-            uint32_t aux = 0;
-            int n_out = (int)take;
-            if (first && self) { aux |= MD_SELF; ++n_out; }
-            if (first && one) { aux |= MD_ONE; ++n_out; }
-            aux |= (uint32_t)take << 8;
-            if (n_out > 0) {
-                mdot_at.push_back(P.ins.size());
-                mdot_refs.emplace_back(partners.begin() + done, partners.begin() + done + take);
-                emit(RR_W0(dd ? RI_MDOTDD : RI_MDOT, aux), 0, 0.0, (dd ? 10.0 : 1.0) * n_out);
-                for (int i = 0; i < n_out; ++i) {
-                    ids.push_back(P.n_dots);
-                    P.n_dots += step;
+        if (dd) {
+            size_t done = 0;
+            bool first = true;
+            do {
+                const size_t take = std::min<size_t>(MD_MAX_PARTNERS, partners.size() - done);
+                uint32_t aux = 0;
+                int n_out = (int)take;
+                if (first && self) { aux |= MD_SELF; ++n_out; }
+                if (first && one) { aux |= MD_ONE; ++n_out; }
+                aux |= (uint32_t)take << 8;
+                if (n_out > 0) {
+                    for (size_t j = done; j < done + take; ++j)
+                        if (partners[j] & PINREF) { err = "internal: pinned partner in a double-double plan"; return; }
+                    mdot_at.push_back(P.ins.size());
+                    mdot_refs.emplace_back(partners.begin() + done, partners.begin() + done + take);
+                    emit(RR_W0(RI_MDOTDD, aux), 0, 0.0, 10.0 * n_out);
+                    for (int i = 0; i < n_out; ++i) {
+                        ids.push_back(P.n_dots);
+                        P.n_dots += 2;
+                    }
+                    P.n_dot_ins += n_out;
                 }
-                P.n_dot_ins += n_out;
+                done += take;
+                first = false;
+            } while (done < partners.size());
+            return;
+        }
+        // pinned partners ride in the mask of RI_MDOT (outputs: self, one, pins ascending; at most
+        // RR_MDOT_MAX_OUT per instruction); every other partner is one RI_DOTM
+        const size_t id0 = ids.size();
+        ids.resize(id0 + (self ? 1 : 0) + (one ? 1 : 0) + partners.size(), DOT_NONE);
+        const size_t part0 = id0 + (self ? 1 : 0) + (one ? 1 : 0);
+        int32_t pin_pos[RR_NPIN];
+        for (int j = 0; j < RR_NPIN; ++j) pin_pos[j] = -1;
+        for (size_t i = 0; i < partners.size(); ++i)
+            if (partners[i] & PINREF) {
+                const int j = (int)(partners[i] & 0xff);
+                if (pin_pos[j] >= 0) { err = "internal: duplicate pinned partner"; return; }
+                pin_pos[j] = (int32_t)i;
             }
-            done += take;
-            first = false;
-        } while (done < partners.size());
+        bool want_self = self, want_one = one;
+        int j = 0;
+        for (;;) {
+            uint32_t aux = 0;
+            int n_out = 0;
+            std::vector<size_t> slots_out;  // positions in ids, emission order
+            if (want_self) { aux |= MD_SELF; slots_out.push_back(id0); ++n_out; want_self = false; }
+            if (want_one) { aux |= MD_ONE; slots_out.push_back(id0 + (self ? 1 : 0)); ++n_out; want_one = false; }
+            for (; j < RR_NPIN && n_out < (int)RR_MDOT_MAX_OUT; ++j)
+                if (pin_pos[j] >= 0) {
+                    aux |= 1u << (8 + j);
+                    slots_out.push_back(part0 + (size_t)pin_pos[j]);
+                    ++n_out;
+                }
+            if (n_out == 0) break;
+            emit(RR_W0(RI_MDOT, aux), 0, 0.0, 1.0 * n_out);
+            for (size_t q : slots_out) ids[q] = P.n_dots++;
+            P.n_dot_ins += n_out;
+            bool more = false;
+            for (int jj = j; jj < RR_NPIN; ++jj) more = more || pin_pos[jj] >= 0;
+            if (!more) break;
+        }
+        for (size_t i = 0; i < partners.size(); ++i)
+            if (!(partners[i] & PINREF)) {
+                emit(RI_DOTM, partners[i], 0.0, 1.0);
+                ids[part0 + i] = P.n_dots++;
+                P.n_dot_ins += 1;
+            }
     }
     int32_t clsmet(uint32_t y_ref)
     {
@@ -457,21 +603,15 @@ struct BatchPlanner::Chunk {
     {
         emit(RI_END, 0, 0.0, 0);
         const int32_t n_cols = (int32_t)colmap.size();
-        auto patch = [&](uint32_t v) -> uint32_t { return (v & STAGED) ? (v & 0x7fffu) : (uint32_t)n_cols + v; };
+        auto patch = [&](uint32_t v) -> uint32_t { return (v & STAGED) ? (v & 0x3fffu) : (uint32_t)n_cols + v; };
         for (size_t i = pc_begin; i < P.ins.size(); ++i) {
             RRIns &x = P.ins[i];
-            bool has_col = false;
-            switch (RR_OP(x.w0)) {
-            case RI_LOAD_M: case RI_ST: case RI_ADD_M: case RI_SUB_M: case RI_RSUB_M: case RI_MUL_M:
-            case RI_DIV_M: case RI_RDIV_M: case RI_AXPY: case RI_CLSMET:
-                has_col = true;
-                break;
-            case RI_RARE:
-                has_col = !(RR_AUX(x.w0) & RB_CONST);
-                break;
-            default:
-                break;
-            }
+            const uint32_t op = RR_OP(x.w0);
+            bool has_col = op >= RI_FIRST_M || op == RI_ST || op == RI_CLSMET;
+            if (op == RI_RARE) has_col = !(RR_AUX(x.w0) & RB_CONST);
+            // the operand of the instruction after USEP comes from the pin: its column field stays 0
+            if (has_col && i > (size_t)pc_begin && RR_OP(P.ins[i - 1].w0) >= RI_USEP0 && RR_OP(P.ins[i - 1].w0) < RI_USEP0 + RR_NPIN)
+                has_col = false;
             if (has_col) x.w1 = patch(x.w1);
         }
         for (size_t k = 0; k < mdot_at.size(); ++k) {
@@ -481,27 +621,6 @@ struct BatchPlanner::Chunk {
             x.w1 = (uint32_t)p[0] | ((uint32_t)p[1] << 16);
             const uint64_t hi = (uint64_t)p[2] | ((uint64_t)p[3] << 16) | ((uint64_t)p[4] << 32) | ((uint64_t)p[5] << 48);
             std::memcpy(&x.imm, &hi, 8);
-        }
-        // peephole: "ST s; MDOT" and "LOAD_M s; MDOT" become one instruction (the tile column rides in
-        // the top byte of w0): one dispatch less for the two most frequent instruction pairs
-        {
-            std::vector<RRIns> out;
-            out.reserve(P.ins.size() - pc_begin);
-            for (size_t i = pc_begin; i < P.ins.size(); ++i) {
-                const RRIns &x = P.ins[i];
-                const uint32_t op = RR_OP(x.w0);
-                if ((op == RI_ST || op == RI_LOAD_M) && i + 1 < P.ins.size() && RR_OP(P.ins[i + 1].w0) == RI_MDOT &&
-                    x.w1 < 256 && !(RR_AUX(P.ins[i + 1].w0) & (MD_ST | MD_LD))) {
-                    RRIns m = P.ins[i + 1];
-                    m.w0 |= ((op == RI_ST ? MD_ST : MD_LD) << 8) | (x.w1 << 24);
-                    out.push_back(m);
-                    ++i;
-                    continue;
-                }
-                out.push_back(x);
-            }
-            P.ins.resize(pc_begin);
-            P.ins.insert(P.ins.end(), out.begin(), out.end());
         }
         RRChunk c;
         std::memset(&c, 0, sizeof(c));
@@ -615,11 +734,17 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
         units[i].w = cand_w_[c];
     }
     const int32_t need = max_need(*this, units);
+    // double-double reductions read tile columns only; otherwise cached terms and the centred target
+    // live in pins and the tile only holds the spill temporaries and the overflow
+    const int32_t pins = dd ? 0 : std::min<int32_t>(std::max(lim.n_pins, 0), RR_NPIN);
     // slots wanted: all terms of the widest candidate resident + spill temporaries; if the tile
     // cannot give that, pairs are scheduled in blocks (see below)
-    const int32_t min_slots = std::min(std::max(4, need + 3), std::max(4, lim.tile_cols / 2));
+    const int32_t min_slots = pins > 1 ? need + 1 + (pins < 4 ? 3 : 0)
+                                       : std::min(std::max(4, need + 3), std::max(4, lim.tile_cols / 2));
     std::vector<ChunkSpec> specs;
-    std::string err = cut_chunks(*this, units, lim, {cols.yc}, min_slots, specs);
+    std::vector<int32_t> always;
+    if (pins == 0) always.push_back(cols.yc);
+    std::string err = cut_chunks(*this, units, lim, always, min_slots, specs);
     if (!err.empty()) return err;
 
     cand_dot.clear();
@@ -635,8 +760,8 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
     std::vector<uint64_t> pkeys;
     std::vector<int32_t> ids;
     for (const ChunkSpec &cs : specs) {
-        Chunk ch(*this, P, lim, cs.cols);
-        const uint32_t yc_col = ch.staged(cols.yc);
+        Chunk ch(*this, P, lim, cs.cols, pins);
+        const uint32_t yc_loc = pins > 0 ? ch.reserve_pin_global(cols.yc) : ch.staged(cols.yc);
         for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
             const std::vector<int32_t> &T = units[ui].terms;
             const int32_t m = (int32_t)T.size();
@@ -650,8 +775,11 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
                 for (int32_t j = 0; j < m && !miss; ++j) miss = missing(T[i], T[j]);
                 if (miss && std::find(N.begin(), N.end(), T[i]) == N.end()) N.push_back(T[i]);
             }
+            // resident terms first: what is new in this candidate then meets all of its partners in ONE
+            // reduction instruction while it is in t, instead of being loaded back once per partner
+            std::stable_partition(N.begin(), N.end(), [&](int32_t u) { return ch.resident(u); });
             ch.unpin_all();
-            const int32_t room = ch.pool_cap - (need + 1);
+            const int32_t room = ch.free_pins() + ch.pool_cap - (need + 1);
             if (room < 2) return "tile too small";
             // t = u; reductions of u with itself, ones, yc and every partner already resident
             auto reduce_term = [&](int32_t u, const std::vector<int32_t> &done) {
@@ -668,16 +796,17 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
                 ch.ensure_tos(u);
                 partners.clear();
                 pkeys.clear();
-                if (with_yc) { partners.push_back(yc_col); pkeys.push_back(key(u, KEY_YC)); }
+                if (with_yc) { partners.push_back(yc_loc); pkeys.push_back(key(u, KEY_YC)); }
                 for (int32_t v : done) {
                     if (v == u || !missing(u, v)) continue;
-                    const int32_t sv = ch.lookup(v);
+                    const int64_t sv = ch.lookup(v);
                     if (sv < 0) { ch.err = "internal: partner not resident"; return; }
                     partners.push_back((uint32_t)sv);
                     pkeys.push_back(key(u, v));
                 }
                 ids.clear();
                 ch.mdot(self, one, partners, dd, ids);
+                if (!ch.err.empty()) return;
                 size_t q = 0;
                 if (self) dots[key(u, u)] = ids[q++];
                 if (one) dots[key(u, KEY_ONE)] = ids[q++];
@@ -749,7 +878,7 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
     std::vector<uint32_t> partners;
     std::vector<int32_t> ids;
     for (const ChunkSpec &cs : specs) {
-        Chunk ch(*this, P, lim, cs.cols);
+        Chunk ch(*this, P, lim, cs.cols, 0);
         const uint32_t y_col = ch.staged(cols.y);
         for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
             const int32_t c = subset[ui];
@@ -793,7 +922,7 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
                 ch.free_slot(acc);
                 continue;
             }
-            std::vector<int32_t> slot(m);
+            std::vector<uint32_t> slot(m);
             for (int32_t i = 0; i < m; ++i) {
                 slot[i] = ch.ensure(T[i]);
                 if (!ch.err.empty()) return ch.err;
@@ -851,7 +980,7 @@ std::string BatchPlanner::plan_eval(const PlanLimits &lim, const ColIds &cols, b
     std::unordered_map<int32_t, int32_t> done;  // identical programs share their result
     std::vector<int32_t> ids;
     for (const ChunkSpec &cs : specs) {
-        Chunk ch(*this, P, lim, cs.cols);
+        Chunk ch(*this, P, lim, cs.cols, 0);
         const uint32_t y_col = ch.staged(cols.y);
         for (int32_t c = cs.begin; c < cs.end; ++c) {
             const int32_t u = units[c].terms[0];
@@ -890,7 +1019,7 @@ std::string BatchPlanner::plan_materialise(const PlanLimits &lim, const ColIds &
     std::string err = cut_chunks(*this, units, lim, {}, need + 2, specs);
     if (!err.empty()) return err;
     for (const ChunkSpec &cs : specs) {
-        Chunk ch(*this, P, lim, cs.cols);
+        Chunk ch(*this, P, lim, cs.cols, 0);
         for (int32_t u = cs.begin; u < cs.end; ++u) {
             ch.unpin_all();
             ch.gen_term(u);
@@ -920,7 +1049,7 @@ template <typename T> T *dup_vec(const std::vector<T> &v)
 }  // namespace
 
 extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kind, int32_t tile_cols,
-                                   int32_t max_slots, int32_t target_chunks, int32_t no_cse,
+                                   int32_t max_slots, int32_t target_chunks, int32_t no_cse, int32_t n_pins,
                                    const double *coef_snapped, rr_debug_plan *out)
 {
     if (!batch || !out) return RR_ERR_INVALID;
@@ -935,6 +1064,7 @@ extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kin
         if (max_slots > 0) lim.max_slots = max_slots;
         lim.target_chunks = std::max(1, target_chunks);
         lim.no_cse = no_cse != 0;
+        lim.n_pins = n_pins;
         rr::ColIds cols{d, d + 1};
         switch (kind) {
         case 0: err = bp.plan_gram(lim, cols, nullptr, false, P, tab, tab_begin); break;

@@ -59,6 +59,7 @@ struct PlanLimits {
     int32_t tile_cols = 56;  // columns that fit the shared-memory tile for the chosen tile height
     int32_t max_slots = 1 << 20;  // cap on value slots (cached terms + temporaries) per chunk: bounds the tile
     int32_t target_chunks = 1;
+    int32_t n_pins = RR_NPIN;     // pins the Gram plans may use (rr_isa.h); 0 = tile slots only
     bool no_cse = false;
 };
 

@@ -10,12 +10,12 @@
 //   The per-sample state is the fp64 accumulator t[S] in registers; operands are tile columns
 //   (conflict-free: lane <-> sample) or immediates, so X and y are read from HBM exactly once
 //   per sweep.
-//   A reduction (MDOT) forms the thread's partial sum over its S samples and feeds a
-//   register-resident binary-counter butterfly: after 32 reductions each lane holds the warp
-//   total of one of them (31 shuffle+add steps for 32 reductions instead of 160), which is added
-//   with one coalesced fire-and-forget RED.ADD.F64 to the warp's PRIVATE accumulator row in global
-//   memory (deterministic: one writer per address, fixed order). Rows are summed by
-//   rr_reduce_rows afterwards.
+//   Reduction partners that many terms share (base-solution terms, centred target) live in 8 per-sample
+//   pin registers; a reduction (RI_MDOT / RI_DOTM) forms the thread's partial over its S samples and
+//   parks it in the warp's shared-memory ring; every 8 reductions the warp transposes the ring and adds
+//   the 8 warp totals with RED.ADD.F64 to the warp's PRIVATE accumulator row in global memory
+//   (deterministic: one writer per address, fixed order; details in rr_sweep_core.cuh). Rows are summed
+//   by rr_reduce_rows afterwards.
 //
 // Semantics per opcode follow node::evaluate_inner, /root/reference/rils_rols_cpp/node.cpp:23-95
 // (IEEE +,-,*,/ and sqrt are bit-identical to the CPU; sin/cos/log/exp/pow are CUDA libdevice,
@@ -32,8 +32,14 @@
 
 namespace rr {
 
-constexpr int kInsWindow = 256;  // instructions per shared-memory window (4 KB), two windows
-constexpr size_t kSweepStaticSmem = 2 * (kInsWindow + 1) * 16 + 2 * 2048 + 256;  // windows + combine buffers + mbarriers
+constexpr int kInsWindow = 128;  // instructions per shared-memory window (2 KB), two windows
+// Shared memory of a block besides its tile. Static: instruction windows + mbarriers. Dynamic, in front of
+// the tile: the reduction rings, 4 KB per warp, aligned to 4096 bytes of the shared WINDOW at run time
+// (the PTX core wraps its ring pointer with one LOP3, which needs that alignment; static __align__ is
+// relative to a section that starts 1 KB into the window) — hence up to 4 KB of alignment slack.
+constexpr size_t sweep_static_smem() { return 2 * (kInsWindow + 1) * 16 + 256; }
+constexpr size_t sweep_ring_smem(int warps) { return (size_t)warps * 4096 + 4096; }
+constexpr size_t sweep_fixed_smem(int warps) { return sweep_static_smem() + sweep_ring_smem(warps); }
 
 struct SweepArgs {
     const double *X;        // engine matrix: columns (features, y, yc) of `ld` doubles
@@ -121,91 +127,102 @@ __device__ __forceinline__ void dd_add(double &hi, double &lo, double h2, double
     lo = t - (hi - s);
 }
 
-// level-l combine of the butterfly: lanes with the mask bit clear keep the EARLIER reduction
-__device__ __forceinline__ double bfly(double pending, double x, bool upper, int mask)
+// rarely generated binary operators (node.cpp:56-93), operand order already resolved
+__device__ __forceinline__ double rr_rare(uint32_t which, double x, double u)
 {
-    const double send = upper ? pending : x;
-    const double keep = upper ? x : pending;
-    return keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    switch (which) {
+    case RR_POW: return pow(x, u);
+    case RR_LT: return x < u ? 1.0 : 0.0;
+    case RR_GT: return x > u ? 1.0 : 0.0;
+    case RR_EQ: return x == u ? 1.0 : 0.0;
+    case RR_NE: return x != u ? 1.0 : 0.0;
+    case RR_MIN: return x < u ? x : u;  // a < b ? a : b, node.cpp:82
+    default: return x > u ? x : u;      // a > b ? a : b, node.cpp:88
+    }
 }
 
-// Transcendental and rarely generated operators run out of line on a per-thread scratch column of
-// the tile: the caller parks t[] there, this function transforms it in place, the caller reloads.
-// Keeping libdevice's branchy bodies out of the interpreter loop lets ptxas keep the accumulator
-// in fixed registers for the cheap operators (the common case) instead of shuffling copies around
-// every dispatch.
-template <int S, int TH>
-__device__ __noinline__ void rr_slow_op(uint32_t scratch, uint32_t w0, uint32_t operand, double imm)
+// The warp's reduction ring (see rr_sweep_core.cuh): 16 rows of 32 lanes. C++ twin of the PTX code,
+// used by the generic interpreter and to drain what is pending at the end of a tile.
+struct RingCtx {
+    uint32_t ring_w;         // warp ring base | lane * 8 (shared-space byte address, base 4096-aligned)
+    uint32_t ra[4];          // this lane's 4 read addresses in ring half 0 when the warp transposes
+    double *acc_row;         // the warp's private accumulator row (+ chunk dot_base)
+    uint32_t lane;
+};
+__device__ __forceinline__ void ring_flush(const RingCtx &rc, uint32_t cnt, uint32_t &fl)
 {
-    constexpr uint32_t SSTR = TH * 8u;
-    const uint32_t op = w0 & 0xffu, aux = w0 >> 8;
-#pragma unroll(S <= 2 ? S : 1)
-    for (int s = 0; s < S; ++s) {
-        double x = lds_f64(scratch + s * SSTR);
-        double r;
-        switch (op) {
-        case RI_SIN: r = sin(x); break;
-        case RI_COS: r = cos(x); break;
-        case RI_LN: r = log(x); break;
-        case RI_EXP: r = exp(x); break;
-        default: {  // RI_RARE
-            double u = (aux & RB_CONST) ? imm : lds_f64(operand + s * SSTR);
-            if (aux & RB_SWAP) {
-                const double tmp = x;
-                x = u;
-                u = tmp;
-            }
-            switch (aux & 0xfu) {
-            case RR_POW: r = pow(x, u); break;
-            case RR_LT: r = x < u ? 1.0 : 0.0; break;
-            case RR_GT: r = x > u ? 1.0 : 0.0; break;
-            case RR_EQ: r = x == u ? 1.0 : 0.0; break;
-            case RR_NE: r = x != u ? 1.0 : 0.0; break;
-            case RR_MIN: r = x < u ? x : u; break;  // a < b ? a : b, node.cpp:82
-            default: r = x > u ? x : u; break;      // a > b ? a : b, node.cpp:88
-            }
-            break;
-        }
-        }
-        sts_f64(scratch + s * SSTR, r);
-    }
+    __syncwarp();
+    const uint32_t h = (fl & 8u) << 8;
+    double f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(f[2 * i]), "=d"(f[2 * i + 1]) : "r"(rc.ra[i] + h));
+    double s = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    const uint32_t idx = fl + (rc.lane & 7u);
+    if (rc.lane < 8u && idx < cnt) atomicAdd(rc.acc_row + idx, s);  // RED.E.ADD.F64, one writer per address
+    fl += 8;
+    __syncwarp();
+}
+__device__ __forceinline__ void ring_emit(const RingCtx &rc, uint32_t &cnt, uint32_t &fl, double v)
+{
+    sts_f64(rc.ring_w + ((cnt & 15u) << 8), v);
+    ++cnt;
+    if (cnt - fl >= 8u) ring_flush(rc, cnt, fl);
 }
 
 // SPECIAL = false: the production interpreter. SPECIAL = true additionally understands the
 // double-double reductions (escalation plans) and the classifier-metric reduction; those plans are
 // rare and run through a separate instantiation so their code does not burden the common one.
+//
+// Sample ownership: with S == 4 a thread owns the pairs (2 tid, 2 tid + 1) of both halves of the tile
+// (two LDS.128 per operand); otherwise samples tid + s * TH.
 template <int S, int TH, bool SPECIAL>
-__global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(const SweepArgs a, const int scratch_col)
+__global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(const SweepArgs a)
 {
     constexpr int T = TH * S;
     constexpr int NW = TH / 32;
-    constexpr int LOG2T = (T == 128 ? 7 : T == 256 ? 8 : T == 512 ? 9 : T == 1024 ? 10 : 11);
-    static_assert((1 << LOG2T) == T, "tile height must be a power of two");
-    extern __shared__ __align__(128) double rr_tile[];  // [columns][T]
+    constexpr bool PAIRS = (S == 4);
+    constexpr uint32_t COLB = T * 8u;   // bytes per tile column
+    constexpr uint32_t HALFB = T * 4u;  // byte offset of the second half of a column
+    extern __shared__ __align__(128) unsigned char rr_dyn[];  // [slack][rings: NW x 16 rows x 32 lanes][tile: columns x T]
     __shared__ __align__(16) uint4 ibuf[2][kInsWindow + 1];
-    __shared__ __align__(16) double red[2][8][32];  // cross-warp combine of finished reductions
     __shared__ __align__(8) uint64_t mbar_tile;
     __shared__ __align__(8) uint64_t mbar_ins[2];
 
     const RRChunk ch = a.chunks[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *acc_row = a.acc + (size_t)blockIdx.x * (size_t)a.acc_stride + ch.dot_base;  // one row per block
     const uint4 *prog = reinterpret_cast<const uint4 *>(a.ins + ch.pc_begin);
     const int n_win = (ch.n_ins + kInsWindow - 1) / kInsWindow;
-    const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4, up2 = lane & 2, up1 = lane & 1;
-    const uint32_t out_slot = __brev((uint32_t)lane) >> 27;  // lane L ends up with reduction bitrev5(L)
-    const uint32_t tile_sh = smem_u32(rr_tile) + (uint32_t)tid * 8u;  // this thread's row 0 of column 0
-    const uint32_t red_sh = smem_u32(&red[0][warp][out_slot]);
-    const uint32_t not_warp0 = warp != 0;
-    constexpr uint32_t CSH = LOG2T + 3;                               // log2(bytes per tile column)
-    constexpr uint32_t SSTR = TH * 8u;                                // byte stride between a thread's samples
-    const uint32_t scratch = tile_sh + ((uint32_t)scratch_col << CSH);
+    // this thread's byte offset inside a column, and of its sample s relative to that
+    const uint32_t tbase = PAIRS ? (uint32_t)tid * 16u : (uint32_t)tid * 8u;
+    auto soff = [](int s) -> uint32_t {
+        return PAIRS ? (uint32_t)(s >> 1) * HALFB + (uint32_t)(s & 1) * 8u : (uint32_t)s * (TH * 8u);
+    };
+    const uint32_t dyn_sh = smem_u32(rr_dyn);
+    const uint32_t ring_sh = (dyn_sh + 4095u) & ~4095u;  // rings of warps 0..NW-1, each 4096-aligned
+    double *const rr_tile = reinterpret_cast<double *>(rr_dyn + (ring_sh - dyn_sh) + NW * 4096u);
+    const uint32_t tile_sh = ring_sh + NW * 4096u + tbase;
+    RingCtx rc;
+    rc.lane = (uint32_t)lane;
+    rc.ring_w = ring_sh + (uint32_t)warp * 4096u + (uint32_t)lane * 8u;
+    {
+        const uint32_t r = lane & 7, q = lane >> 3;
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i)
+            rc.ra[i] = ring_sh + (uint32_t)warp * 4096u + r * 256u + (((4u * q + i + r) & 15u) << 4);
+    }
+    rc.acc_row = a.acc + ((size_t)blockIdx.x * NW + warp) * (size_t)a.acc_stride + ch.dot_base;  // one row per warp
 
     if (tid == 0) {
         mbar_init(&mbar_tile, 1);
         mbar_init(&mbar_ins[0], 1);
         mbar_init(&mbar_ins[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the sentinel behind each window: never overwritten by the window copies
+        ibuf[0][kInsWindow] = make_uint4(RI_WINEND, 0, 0, 0);
+        ibuf[1][kInsWindow] = make_uint4(RI_WINEND, 0, 0, 0);
     }
     __syncthreads();
     uint32_t tile_parity = 0, ins_parity0 = 0, ins_parity1 = 0;
@@ -222,7 +239,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
             }
             __syncwarp();
             for (int c = lane; c < ch.n_cols; c += 32)
-                tma_load_1d(rr_tile + ((size_t)c << LOG2T), a.X + (size_t)a.cols[ch.col_begin + c] * a.ld + base,
+                tma_load_1d(rr_tile + (size_t)c * T, a.X + (size_t)a.cols[ch.col_begin + c] * a.ld + base,
                             (uint32_t)(T * 8), &mbar_tile);
         }
         mbar_wait(&mbar_tile, tile_parity);
@@ -231,41 +248,22 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         const bool partial = base + T > a.n;
         bool valid[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) valid[s] = base + tid + s * TH < a.n;
+        for (int s = 0; s < S; ++s) valid[s] = base + (int64_t)((tbase + soff(s)) >> 3) < a.n;
+        const double *xg = a.X + base + (tbase >> 3);  // this thread's first sample in engine column 0
 
         double t[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) t[s] = 0.0;
-        double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0, l4 = 0.0;  // butterfly levels
-        uint32_t cnt = 0;                                          // reductions emitted in this chunk
+        uint32_t cnt = 0, fl = 0;  // reductions emitted / flushed in this chunk and tile
         uint32_t ddcnt = 0;
-
-// feeds one reduction into the butterfly (named registers only: nothing is indexed dynamically)
-#define RR_EMIT(val)                                                                         \
-    do {                                                                                     \
-        double x_ = (val);                                                                   \
-        const uint32_t c_ = cnt++;                                                           \
-        if (!(c_ & 1u)) { l0 = x_; break; }                                                  \
-        x_ = bfly(l0, x_, up16, 16);                                                         \
-        if (!(c_ & 2u)) { l1 = x_; break; }                                                  \
-        x_ = bfly(l1, x_, up8, 8);                                                           \
-        if (!(c_ & 4u)) { l2 = x_; break; }                                                  \
-        x_ = bfly(l2, x_, up4, 4);                                                           \
-        if (!(c_ & 8u)) { l3 = x_; break; }                                                  \
-        x_ = bfly(l3, x_, up2, 2);                                                           \
-        if (!(c_ & 16u)) { l4 = x_; break; }                                                 \
-        x_ = bfly(l4, x_, up1, 1);                                                           \
-        /* 32 reductions done: combine the block's warps in fixed order, one RED per reduction */ \
-        const uint32_t buf_ = (c_ >> 5) & 1u;                                                \
-        red[buf_][warp][out_slot] = x_;                                                      \
-        __syncthreads();                                                                     \
-        if (warp == 0) {                                                                     \
-            double s_ = red[buf_][0][out_slot];                                              \
-            for (int w_ = 1; w_ < NW; ++w_) s_ += red[buf_][w_][out_slot];                   \
-            const uint32_t idx_ = (c_ & ~31u) + out_slot;                                    \
-            if ((int32_t)idx_ < ch.n_dots) atomicAdd(acc_row + idx_, s_); /* RED.E.ADD.F64 */ \
-        }                                                                                    \
-    } while (0)
+        // pins: registers of the PTX core (static indices only) or a local array of the generic path
+        double pr[PAIRS ? RR_NPIN * 4 : 1];
+        double pl[RR_NPIN][S];
+        if constexpr (PAIRS) {
+#pragma unroll
+            for (int i = 0; i < RR_NPIN * 4; ++i) pr[i] = 0.0;
+        }
+        int use_pin = -1;  // generic path: pin redirected into the next tile-column operand
 
         bool running = true;
         for (int win = 0; running; ++win) {
@@ -281,50 +279,49 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
             if (b == 0) { mbar_wait(&mbar_ins[0], ins_parity0); ins_parity0 ^= 1u; }
             else { mbar_wait(&mbar_ins[1], ins_parity1); ins_parity1 ^= 1u; }
             const uint4 *ib = ibuf[b];
-            if constexpr (!SPECIAL && S <= 4) {
+            if constexpr (!SPECIAL && PAIRS) {
                 if (!partial) {
                     // full tile: the PTX core runs the window; it hands back what it does not implement
                     uint32_t ibp = smem_u32(ib);
-                    const uint32_t ib_end = ibp + kInsWindow * 16u;
-                    double t0 = t[0], t1 = t[S > 1 ? 1 : 0], t2 = t[S > 2 ? 2 : 0], t3 = t[S > 3 ? 3 : 0];
+                    double t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3];
                     for (;;) {
                         uint32_t w0, w1;
                         double imm;
-                        uint32_t code;
-#define RR_CORE_ARGS t0, t1, t2, t3, l0, l1, l2, l3, l4, cnt, ibp, w0, w1, imm, ib_end, tile_sh, acc_row, ch.n_dots, \
-                     out_slot, (uint32_t)lane, red_sh, not_warp0
-                        if constexpr (S == 1 && NW == 4) code = rr_core_s1_w4<SSTR, CSH>(RR_CORE_ARGS);
-                        else if constexpr (S == 2 && NW == 4) code = rr_core_s2_w4<SSTR, CSH>(RR_CORE_ARGS);
-                        else if constexpr (S == 4 && NW == 4) code = rr_core_s4_w4<SSTR, CSH>(RR_CORE_ARGS);
-                        else if constexpr (S == 1) code = rr_core_s1_w8<SSTR, CSH>(RR_CORE_ARGS);
-                        else if constexpr (S == 2) code = rr_core_s2_w8<SSTR, CSH>(RR_CORE_ARGS);
-                        else code = rr_core_s4_w8<SSTR, CSH>(RR_CORE_ARGS);
-#undef RR_CORE_ARGS
+                        const uint32_t code = rr_core_s4<COLB, HALFB>(t0, t1, t2, t3, pr, cnt, fl, ibp, w0, w1, imm, tile_sh,
+                                                                      rc.ring_w, rc.acc_row, rc.lane, rc.ra[0], rc.ra[1],
+                                                                      rc.ra[2], rc.ra[3], xg, a.ld * 8);
                         if (code == 0) break;
                         if (code == 1) { running = false; break; }
-                        const uint32_t col = tile_sh + (w1 << CSH);
-                        if ((w0 & 0xffu) == RI_STG) {
-                            double *p = a.stg + (size_t)w1 * a.ld_stg + base + tid;
-                            p[0] = t0;
-                            if (S > 1) p[TH] = t1;
-                            if (S > 2) p[2 * TH] = t2;
-                            if (S > 3) p[3 * TH] = t3;
-                        } else {
-                            sts_f64(scratch, t0);
-                            if (S > 1) sts_f64(scratch + SSTR, t1);
-                            if (S > 2) sts_f64(scratch + 2 * SSTR, t2);
-                            if (S > 3) sts_f64(scratch + 3 * SSTR, t3);
-                            rr_slow_op<S, TH>(scratch, w0, col, imm);
-                            t0 = lds_f64(scratch);
-                            if (S > 1) t1 = lds_f64(scratch + SSTR);
-                            if (S > 2) t2 = lds_f64(scratch + 2 * SSTR);
-                            if (S > 3) t3 = lds_f64(scratch + 3 * SSTR);
+                        switch (w0 & 0xffu) {
+                        case RI_STG: {
+                            double *p = a.stg + (size_t)w1 * a.ld_stg + base + (tbase >> 3);
+                            *reinterpret_cast<double2 *>(p) = make_double2(t0, t1);
+                            *reinterpret_cast<double2 *>(p + T / 2) = make_double2(t2, t3);
+                            break;
+                        }
+                        // four independent evaluations: the compiler interleaves them
+                        case RI_SIN: t0 = sin(t0); t1 = sin(t1); t2 = sin(t2); t3 = sin(t3); break;
+                        case RI_COS: t0 = cos(t0); t1 = cos(t1); t2 = cos(t2); t3 = cos(t3); break;
+                        case RI_LN: t0 = log(t0); t1 = log(t1); t2 = log(t2); t3 = log(t3); break;
+                        case RI_EXP: t0 = exp(t0); t1 = exp(t1); t2 = exp(t2); t3 = exp(t3); break;
+                        case RI_RARE: {
+                            const uint32_t aux = w0 >> 8;
+                            const uint32_t col = tile_sh + w1 * COLB;
+                            double u0 = imm, u1 = imm, u2 = imm, u3 = imm;
+                            if (!(aux & RB_CONST)) {
+                                u0 = lds_f64(col); u1 = lds_f64(col + 8); u2 = lds_f64(col + HALFB); u3 = lds_f64(col + HALFB + 8);
+                            }
+                            const bool sw = aux & RB_SWAP;
+                            t0 = sw ? rr_rare(aux & 0xfu, u0, t0) : rr_rare(aux & 0xfu, t0, u0);
+                            t1 = sw ? rr_rare(aux & 0xfu, u1, t1) : rr_rare(aux & 0xfu, t1, u1);
+                            t2 = sw ? rr_rare(aux & 0xfu, u2, t2) : rr_rare(aux & 0xfu, t2, u2);
+                            t3 = sw ? rr_rare(aux & 0xfu, u3, t3) : rr_rare(aux & 0xfu, t3, u3);
+                            break;
+                        }
+                        default: break;  // double-double / classifier reductions only exist in SPECIAL plans
                         }
                     }
-                    t[0] = t0;
-                    if (S > 1) t[S > 1 ? 1 : 0] = t1;
-                    if (S > 2) t[S > 2 ? 2 : 0] = t2;
-                    if (S > 3) t[S > 3 ? 3 : 0] = t3;
+                    t[0] = t0; t[S > 1 ? 1 : 0] = t1; t[S > 2 ? 2 : 0] = t2; t[S > 3 ? 3 : 0] = t3;
                     continue;
                 }
             }
@@ -332,12 +329,32 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
 #pragma unroll 1
             for (int pc = 0; pc < kInsWindow; ++pc) {
                 const uint4 in = nx;
-                nx = ib[pc + 1];  // one slot of padding follows each window
+                nx = ib[pc + 1];  // the sentinel slot follows each window
                 const uint32_t w0 = in.x, w1 = in.y;
                 const double imm = __hiloint2double((int)in.w, (int)in.z);
-                const uint32_t col = tile_sh + (w1 << CSH);
-#define COL(s) lds_f64(col + (s) * SSTR)
-                switch (w0 & 0xffu) {
+                const uint32_t col = tile_sh + w1 * COLB;
+                const uint32_t op = w0 & 0xffu;
+                // operand of the tile-column forms: the tile column or, after USEP, a pin
+                double u[S];
+                if (op >= RI_FIRST_M) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) u[s] = use_pin >= 0 ? pl[use_pin][s] : lds_f64(col + soff(s));
+                    use_pin = -1;
+                }
+                if (op >= RI_PIN0 && op < RI_FIRST_M) {
+                    const int j = (int)(op - RI_PIN0) & (RR_NPIN - 1);
+                    if (op < RI_LDP0) {
+#pragma unroll
+                        for (int s = 0; s < S; ++s) pl[j][s] = t[s];
+                    } else if (op < RI_USEP0) {
+#pragma unroll
+                        for (int s = 0; s < S; ++s) t[s] = pl[j][s];
+                    } else {
+                        use_pin = j;
+                    }
+                    continue;
+                }
+                switch (op) {
                 case RI_END:
                     running = false;
                     pc = kInsWindow;
@@ -348,17 +365,23 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     break;
                 case RI_LOAD_M:
 #pragma unroll
-                    for (int s = 0; s < S; ++s) t[s] = COL(s);
+                    for (int s = 0; s < S; ++s) t[s] = u[s];
                     break;
                 case RI_ST:
 #pragma unroll
-                    for (int s = 0; s < S; ++s) sts_f64(col + s * SSTR, t[s]);
+                    for (int s = 0; s < S; ++s) sts_f64(col + soff(s), t[s]);
                     break;
                 case RI_STG: {
-                    double *p = a.stg + (size_t)w1 * a.ld_stg + base + tid;
+                    double *p = a.stg + (size_t)w1 * a.ld_stg + base + (tbase >> 3);
 #pragma unroll
                     for (int s = 0; s < S; ++s)
-                        if (valid[s]) p[s * TH] = t[s];
+                        if (valid[s]) p[soff(s) >> 3] = t[s];
+                    break;
+                }
+                case RI_LDG: {
+                    const double *p = xg + (size_t)w1 * a.ld;  // columns are zero padded to a multiple of 1024 rows
+#pragma unroll
+                    for (int s = 0; s < S; ++s) t[s] = p[soff(s) >> 3];
                     break;
                 }
                 case RI_ADD_C:
@@ -367,7 +390,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     break;
                 case RI_ADD_M:
 #pragma unroll
-                    for (int s = 0; s < S; ++s) t[s] = __dadd_rn(t[s], COL(s));
+                    for (int s = 0; s < S; ++s) t[s] = __dadd_rn(t[s], u[s]);
                     break;
                 case RI_SUB_C:
 #pragma unroll
@@ -375,7 +398,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     break;
                 case RI_SUB_M:
 #pragma unroll
-                    for (int s = 0; s < S; ++s) t[s] = __dsub_rn(t[s], COL(s));
+                    for (int s = 0; s < S; ++s) t[s] = __dsub_rn(t[s], u[s]);
                     break;
                 case RI_RSUB_C:
 #pragma unroll
@@ -383,7 +406,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     break;
                 case RI_RSUB_M:
 #pragma unroll
-                    for (int s = 0; s < S; ++s) t[s] = __dsub_rn(COL(s), t[s]);
+                    for (int s = 0; s < S; ++s) t[s] = __dsub_rn(u[s], t[s]);
                     break;
                 case RI_MUL_C:
 #pragma unroll
@@ -391,7 +414,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     break;
                 case RI_MUL_M:
 #pragma unroll
-                    for (int s = 0; s < S; ++s) t[s] = __dmul_rn(t[s], COL(s));
+                    for (int s = 0; s < S; ++s) t[s] = __dmul_rn(t[s], u[s]);
                     break;
                 case RI_DIV_C:
 #pragma unroll
@@ -399,7 +422,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     break;
                 case RI_DIV_M:
 #pragma unroll
-                    for (int s = 0; s < S; ++s) t[s] = __ddiv_rn(t[s], COL(s));
+                    for (int s = 0; s < S; ++s) t[s] = __ddiv_rn(t[s], u[s]);
                     break;
                 case RI_RDIV_C:
 #pragma unroll
@@ -407,23 +430,37 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     break;
                 case RI_RDIV_M:
 #pragma unroll
-                    for (int s = 0; s < S; ++s) t[s] = __ddiv_rn(COL(s), t[s]);
+                    for (int s = 0; s < S; ++s) t[s] = __ddiv_rn(u[s], t[s]);
                     break;
                 case RI_AXPY:
 #pragma unroll
-                    for (int s = 0; s < S; ++s) t[s] = __dadd_rn(t[s], __dmul_rn(imm, COL(s)));
+                    for (int s = 0; s < S; ++s) t[s] = __dadd_rn(t[s], __dmul_rn(imm, u[s]));
                     break;
                 case RI_SIN:
-                case RI_COS:
-                case RI_LN:
-                case RI_EXP:
-                case RI_RARE:
-#pragma unroll
-                    for (int s = 0; s < S; ++s) sts_f64(scratch + s * SSTR, t[s]);
-                    rr_slow_op<S, TH>(scratch, w0, col, imm);
-#pragma unroll
-                    for (int s = 0; s < S; ++s) t[s] = lds_f64(scratch + s * SSTR);
+#pragma unroll 1
+                    for (int s = 0; s < S; ++s) t[s] = sin(t[s]);
                     break;
+                case RI_COS:
+#pragma unroll 1
+                    for (int s = 0; s < S; ++s) t[s] = cos(t[s]);
+                    break;
+                case RI_LN:
+#pragma unroll 1
+                    for (int s = 0; s < S; ++s) t[s] = log(t[s]);
+                    break;
+                case RI_EXP:
+#pragma unroll 1
+                    for (int s = 0; s < S; ++s) t[s] = exp(t[s]);
+                    break;
+                case RI_RARE: {
+                    const uint32_t aux = w0 >> 8;
+#pragma unroll 1
+                    for (int s = 0; s < S; ++s) {
+                        const double v = (aux & RB_CONST) ? imm : lds_f64(col + soff(s));
+                        t[s] = (aux & RB_SWAP) ? rr_rare(aux & 0xfu, v, t[s]) : rr_rare(aux & 0xfu, t[s], v);
+                    }
+                    break;
+                }
                 case RI_SQRT:
 #pragma unroll
                     for (int s = 0; s < S; ++s) t[s] = sqrt(t[s]);
@@ -432,52 +469,44 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
 #pragma unroll
                     for (int s = 0; s < S; ++s) t[s] = __dmul_rn(t[s], t[s]);
                     break;
+                case RI_DOTM: {
+                    double v = 0.0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s)
+                        if (!partial || valid[s]) v = fma(t[s], u[s], v);
+                    ring_emit(rc, cnt, fl, v);
+                    break;
+                }
                 case RI_MDOT: {
-                    if (w0 & ((MD_ST | MD_LD) << 8)) {
-                        const uint32_t fc = tile_sh + ((w0 >> 24) << CSH);
-                        if (w0 & (MD_ST << 8)) {
-#pragma unroll
-                            for (int s = 0; s < S; ++s) sts_f64(fc + s * SSTR, t[s]);
-                        } else {
-#pragma unroll
-                            for (int s = 0; s < S; ++s) t[s] = lds_f64(fc + s * SSTR);
-                        }
-                    }
                     if (w0 & (MD_SELF << 8)) {
                         double v = 0.0;
 #pragma unroll
                         for (int s = 0; s < S; ++s)
                             if (!partial || valid[s]) v = fma(t[s], t[s], v);
-                        RR_EMIT(v);
+                        ring_emit(rc, cnt, fl, v);
                     }
                     if (w0 & (MD_ONE << 8)) {
                         double v = 0.0;
 #pragma unroll
                         for (int s = 0; s < S; ++s)
                             if (!partial || valid[s]) v += t[s];
-                        RR_EMIT(v);
+                        ring_emit(rc, cnt, fl, v);
                     }
-                    const uint32_t np = (w0 >> 16) & 0xffu;
-                    uint32_t q0 = w1, q1 = in.z, q2 = in.w;  // six 16-bit partner columns
+                    const uint32_t mask = (w0 >> 16) & 0xffu;
 #pragma unroll 1
-                    for (uint32_t j = 0; j < np; ++j) {
-                        const uint32_t p = tile_sh + ((q0 & 0xffffu) << CSH);
-                        q0 = __funnelshift_r(q0, q1, 16);
-                        q1 = __funnelshift_r(q1, q2, 16);
-                        q2 >>= 16;
+                    for (int j = 0; j < RR_NPIN; ++j) {
+                        if (!((mask >> j) & 1u)) continue;
                         double v = 0.0;
 #pragma unroll
-                        for (int s = 0; s < S; ++s) {
-                            const double x = lds_f64(p + s * SSTR);
-                            if (!partial || valid[s]) v = fma(t[s], x, v);
-                        }
-                        RR_EMIT(v);
+                        for (int s = 0; s < S; ++s)
+                            if (!partial || valid[s]) v = fma(t[s], pl[j][s], v);
+                        ring_emit(rc, cnt, fl, v);
                     }
                     break;
                 }
                 case RI_MDOTDD: if constexpr (SPECIAL) {
                     // a double-double plan holds MDOTDD reductions only (rr_plan.cpp): they bypass the
-                    // butterfly; output i occupies the (hi, lo) pair at 2i in the warp's private row
+                    // ring; output i occupies the (hi, lo) pair at 2i in the warp's private row
                     const uint32_t np = (w0 >> 16) & 0xffu;
                     const int has_self = (w0 >> 8) & 1, has_one = (w0 >> 9) & 1;
                     const int n_out = (int)np + has_self + has_one;
@@ -487,7 +516,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                         int kind = 2;  // 0 self, 1 one, 2 column
                         if (has_self && o == 0) kind = 0;
                         else if (has_one && o == has_self) kind = 1;
-                        const uint32_t p = tile_sh + ((q0 & 0xffffu) << CSH);
+                        const uint32_t p = tile_sh + (q0 & 0xffffu) * COLB;
                         if (kind == 2) {
                             q0 = __funnelshift_r(q0, q1, 16);
                             q1 = __funnelshift_r(q1, q2, 16);
@@ -496,27 +525,21 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                         double hi = 0.0, lo = 0.0;
 #pragma unroll
                         for (int s = 0; s < S; ++s)
-                            if (valid[s]) dd_add_prod(hi, lo, t[s], kind == 0 ? t[s] : (kind == 1 ? 1.0 : lds_f64(p + s * SSTR)));
+                            if (valid[s]) dd_add_prod(hi, lo, t[s], kind == 0 ? t[s] : (kind == 1 ? 1.0 : lds_f64(p + soff(s))));
 #pragma unroll
                         for (int m = 16; m > 0; m >>= 1) {
                             const double h2 = __shfl_xor_sync(0xffffffffu, hi, m);
                             const double l2_ = __shfl_xor_sync(0xffffffffu, lo, m);
                             dd_add(hi, lo, h2, l2_);
                         }
-                        // block combine in double-double (fixed warp order), one writer per (hi, lo) pair
+                        // one writer per (hi, lo) pair of the warp's row
                         if (lane == 0) {
-                            red[0][warp][0] = hi;
-                            red[0][warp][1] = lo;
-                        }
-                        __syncthreads();
-                        if (tid == 0) {
-                            double *q = acc_row + 2u * ddcnt;
+                            double *q = rc.acc_row + 2u * ddcnt;
                             double ah = q[0], al = q[1];
-                            for (int w_ = 0; w_ < NW; ++w_) dd_add(ah, al, red[0][w_][0], red[0][w_][1]);
+                            dd_add(ah, al, hi, lo);
                             q[0] = ah;
                             q[1] = al;
                         }
-                        __syncthreads();
                         ++ddcnt;
                     }
                     break;
@@ -527,7 +550,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
                         if (!valid[s]) continue;
-                        const double yp = t[s], yy = COL(s);
+                        const double yp = t[s], yy = lds_f64(col + soff(s));
                         const double ypib = yp >= 0.5 ? 1.0 : 0.0;
                         const double yib = yy >= 0.5 ? 1.0 : 0.0;
                         if (ypib == yib) acc += 1.0;
@@ -536,20 +559,18 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                         ll -= lli;
                         al += fabs(yib - yp);
                     }
-                    RR_EMIT(acc);
-                    RR_EMIT(ll);
-                    RR_EMIT(al);
+                    ring_emit(rc, cnt, fl, acc);
+                    ring_emit(rc, cnt, fl, ll);
+                    ring_emit(rc, cnt, fl, al);
                     break;
                 }
                 default:
                     break;
                 }
-#undef COL
             }
         }
-        // drain the butterfly: pad the last group with zeros
-        while (cnt & 31u) RR_EMIT(0.0);
-#undef RR_EMIT
+        // drain the ring
+        while (fl < cnt) ring_flush(rc, cnt, fl);
         __syncthreads();  // every warp is done with the tile before it is overwritten
     }
 }

@@ -15,9 +15,14 @@ import numpy as np
 from rils_rols_b200 import engine as E
 from rils_rols_b200.batch import Batch, rr_batch
 
-(RI_END, RI_LOAD_C, RI_LOAD_M, RI_ST, RI_STG, RI_ADD_C, RI_ADD_M, RI_SUB_C, RI_SUB_M, RI_RSUB_C, RI_RSUB_M,
- RI_MUL_C, RI_MUL_M, RI_DIV_C, RI_DIV_M, RI_RDIV_C, RI_RDIV_M, RI_AXPY, RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT,
- RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET) = range(28)
+RR_NPIN = 8
+(RI_END, RI_WINEND, RI_LOAD_C, RI_ST, RI_STG, RI_LDG, RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C, RI_RDIV_C,
+ RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET, RI_PIN0) = range(23)
+RI_LDP0 = RI_PIN0 + RR_NPIN
+RI_USEP0 = RI_LDP0 + RR_NPIN
+RI_FIRST_M = RI_USEP0 + RR_NPIN
+(RI_LOAD_M, RI_ADD_M, RI_SUB_M, RI_RSUB_M, RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_AXPY, RI_DOTM) = range(RI_FIRST_M, RI_FIRST_M + 9)
+RR_MDOT_MAX_OUT = 8
 RR_POW, RR_LT, RR_GT, RR_EQ, RR_NE, RR_MIN, RR_MAX = range(7)
 RB_CONST, RB_SWAP = 1 << 4, 1 << 5
 
@@ -39,10 +44,10 @@ class rr_debug_plan(C.Structure):
 
 class Plan:
     def __init__(self, batch: Batch, d: int, kind: int, tile_cols: int = 56, max_slots: int = 0,
-                 target_chunks: int = 1, no_cse: bool = False, coef=None):
+                 target_chunks: int = 1, no_cse: bool = False, coef=None, n_pins: int = RR_NPIN):
         L = E.lib()
         L.rr_debug_plan_batch.argtypes = [C.POINTER(rr_batch), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                          C.c_int32, C.POINTER(C.c_double), C.POINTER(rr_debug_plan)]
+                                          C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(rr_debug_plan)]
         L.rr_debug_plan_batch.restype = C.c_int
         L.rr_debug_plan_free.argtypes = [C.POINTER(rr_debug_plan)]
         L.rr_debug_plan_free.restype = None
@@ -52,8 +57,8 @@ class Plan:
         if coef is not None:
             coef = np.ascontiguousarray(coef, dtype=np.float64)
             cp = coef.ctypes.data_as(C.POINTER(C.c_double))
-        rc = L.rr_debug_plan_batch(C.byref(bs), d, kind, tile_cols, max_slots, target_chunks, int(no_cse), cp,
-                                   C.byref(out))
+        rc = L.rr_debug_plan_batch(C.byref(bs), d, kind, tile_cols, max_slots, target_chunks, int(no_cse),
+                                   int(n_pins), cp, C.byref(out))
         if rc != 0:
             raise ValueError(out.error.decode())
 
@@ -86,6 +91,8 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
             ncols = int(ch["n_cols"])
             tile = {i: cols_global[plan.cols[ch["col_begin"] + i]] for i in range(ncols)}
             t = np.zeros(n)
+            pins = [None] * RR_NPIN
+            use_pin = -1
             out = int(ch["dot_base"])
             pc = int(ch["pc_begin"])
             end = pc + int(ch["n_ins"])
@@ -93,27 +100,47 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 w0, w1, imm = int(plan.ins["w0"][pc]), int(plan.ins["w1"][pc]), float(plan.ins["imm"][pc])
                 pc += 1
                 op, aux = w0 & 0xFF, (w0 >> 8) & 0xFFFF
-                assert w1 < plan.max_tile_cols or op in (RI_STG, RI_MDOT, RI_MDOTDD, RI_END, RI_LOAD_C) or (op % 2 == 1 and RI_ADD_C <= op <= RI_RDIV_C), \
-                    f"tile column {w1} out of range"
+                src = None
+                if op >= RI_FIRST_M:
+                    if use_pin >= 0:
+                        src = pins[use_pin]
+                        assert src is not None, "USEP of an empty pin"
+                    else:
+                        assert w1 < plan.max_tile_cols, f"tile column {w1} out of range"
+                        src = tile[w1]
+                else:
+                    assert use_pin < 0, "USEP must be followed by a tile-column operand form"
+                use_pin = -1
                 if op == RI_END:
                     break
                 elif op == RI_LOAD_C: t = np.full(n, imm)
-                elif op == RI_LOAD_M: t = tile[w1].copy()
-                elif op == RI_ST: tile[w1] = t.copy()
+                elif op == RI_LOAD_M: t = src.copy()
+                elif op == RI_ST:
+                    assert w1 < plan.max_tile_cols, f"tile column {w1} out of range"
+                    tile[w1] = t.copy()
                 elif op == RI_STG: stg[w1] = t
+                elif op == RI_LDG: t = cols_global[w1].copy()
                 elif op == RI_ADD_C: t = t + imm
-                elif op == RI_ADD_M: t = t + tile[w1]
+                elif op == RI_ADD_M: t = t + src
                 elif op == RI_SUB_C: t = t - imm
-                elif op == RI_SUB_M: t = t - tile[w1]
+                elif op == RI_SUB_M: t = t - src
                 elif op == RI_RSUB_C: t = imm - t
-                elif op == RI_RSUB_M: t = tile[w1] - t
+                elif op == RI_RSUB_M: t = src - t
                 elif op == RI_MUL_C: t = t * imm
-                elif op == RI_MUL_M: t = t * tile[w1]
+                elif op == RI_MUL_M: t = t * src
                 elif op == RI_DIV_C: t = t / imm
-                elif op == RI_DIV_M: t = t / tile[w1]
+                elif op == RI_DIV_M: t = t / src
                 elif op == RI_RDIV_C: t = imm / t
-                elif op == RI_RDIV_M: t = tile[w1] / t
-                elif op == RI_AXPY: t = t + imm * tile[w1]
+                elif op == RI_RDIV_M: t = src / t
+                elif op == RI_AXPY: t = t + imm * src
+                elif op == RI_DOTM:
+                    dots[out] += float(np.dot(t, src))
+                    out += 1
+                elif RI_PIN0 <= op < RI_PIN0 + RR_NPIN: pins[op - RI_PIN0] = t.copy()
+                elif RI_LDP0 <= op < RI_LDP0 + RR_NPIN:
+                    assert pins[op - RI_LDP0] is not None, "LDP of an empty pin"
+                    t = pins[op - RI_LDP0].copy()
+                elif RI_USEP0 <= op < RI_USEP0 + RR_NPIN: use_pin = op - RI_USEP0
                 elif op == RI_SIN: t = np.sin(t)
                 elif op == RI_COS: t = np.cos(t)
                 elif op == RI_LN: t = np.log(t)
@@ -131,12 +158,20 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     elif r == RR_NE: t = (x != v).astype(float)
                     elif r == RR_MIN: t = np.where(x < v, x, v)
                     else: t = np.where(x > v, x, v)
-                elif op in (RI_MDOT, RI_MDOTDD):
-                    step = 2 if op == RI_MDOTDD else 1
-                    if aux & 4:
-                        tile[w0 >> 24] = t.copy()
-                    elif aux & 8:
-                        t = tile[w0 >> 24].copy()
+                elif op == RI_MDOT:
+                    vals = []
+                    if aux & 1: vals.append(float(np.dot(t, t)))
+                    if aux & 2: vals.append(float(np.sum(t)))
+                    mask = (aux >> 8) & 0xFF
+                    for j in range(RR_NPIN):
+                        if mask >> j & 1:
+                            assert pins[j] is not None, "MDOT against an empty pin"
+                            vals.append(float(np.dot(t, pins[j])))
+                    assert 0 < len(vals) <= RR_MDOT_MAX_OUT
+                    for v in vals:
+                        dots[out] += v
+                        out += 1
+                elif op == RI_MDOTDD:
                     vals = []
                     if aux & 1: vals.append(float(np.dot(t, t)))
                     if aux & 2: vals.append(float(np.sum(t)))
@@ -147,7 +182,7 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                         vals.append(float(np.dot(t, tile[c])))
                     for v in vals:
                         dots[out] += v
-                        out += step
+                        out += 2
                 elif op == RI_CLSMET:
                     y = tile[w1]
                     ypb, yb = (t >= 0.5).astype(float), (y >= 0.5).astype(float)
