@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -238,42 +240,16 @@ namespace {
 // planned for (bounds the shared-memory tile and therefore the number of value slots)
 struct SweepCfg {
     int S, TH, occ;
+    int slack = 4096;  // bytes between the start of the kernel's dynamic shared memory and the 4096-aligned rings
     int T() const { return S * TH; }
-    size_t dyn_smem_budget() const
+    size_t dyn_smem_budget() const  // for the tile
     {
         const size_t per_block = std::min(kSmemPerBlockMax, kSmemPerSM / (size_t)occ - kSmemReserved);
-        return per_block - rr::sweep_fixed_smem(TH / 32);
+        return per_block - rr::sweep_static_smem() - rr::sweep_ring_smem(TH / 32, slack);
     }
     // columns the planner may use
     int tile_cols() const { return (int)std::min<size_t>(dyn_smem_budget() / ((size_t)T() * 8), 0x3000); }
 };
-
-SweepCfg choose_cfg(const rr_engine *e)
-{
-    SweepCfg c;
-    // 4 samples per thread (the PTX core of rr_sweep_core.cuh) in 128-thread blocks, 2 blocks per SM:
-    // per-dispatch overhead wants more samples per thread, latency hiding wants more warps, and the
-    // shared-memory tile caps the samples in flight per SM (profiles/r1_config_sweep.txt, r2_*)
-    const bool big = e->n >= (1 << 15);
-    c.S = e->s_pref ? e->s_pref : (big ? 4 : 1);
-    c.TH = e->th_pref ? e->th_pref : 128;
-    c.occ = e->occ_pref ? e->occ_pref : (c.T() >= 1024 ? 1 : (c.T() >= 512 ? 2 : (c.T() >= 256 ? 3 : 4)));
-    // the tile must stage the feature columns a chunk can touch plus a few value slots (cached terms
-    // live in pins first)
-    const int want = std::min(e->d, 24) + 3;
-    while (c.tile_cols() < want && c.occ > 1) --c.occ;
-    while (c.tile_cols() < want && c.S > 1) c.S /= 2;
-    return c;
-}
-
-template <typename T> int upload(rr_engine *e, DevBuf &buf, const T *src, size_t count)
-{
-    const size_t bytes = count * sizeof(T);
-    CU(buf.ensure(std::max<size_t>(bytes, 16)));
-    if (bytes) CU(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, e->stream));
-    e->stats.h2d_bytes += bytes;
-    return RR_OK;
-}
 
 using SweepKernel = void (*)(const rr::SweepArgs);
 template <bool SP> SweepKernel sweep_kernel_sel(const SweepCfg &c)
@@ -296,6 +272,60 @@ SweepKernel sweep_kernel_for(const SweepCfg &c, bool special)
     return special ? sweep_kernel_sel<true>(c) : sweep_kernel_sel<false>(c);
 }
 
+// Where does this kernel's dynamic shared memory start in the shared window? (asked once per kernel
+// variant: the kernel reports it in probe mode.) Returns the bytes up to the next multiple of 4096.
+int sweep_slack(rr_engine *e, SweepKernel kern, int TH)
+{
+    static std::mutex mu;
+    static std::map<const void *, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find((const void *)kern);
+    if (it != cache.end()) return it->second;
+    int slack = 4096;
+    if (e->d_misc.ensure(64) == cudaSuccess) {
+        rr::SweepArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.acc = e->d_misc.as<double>();
+        a.n_tiles = -1;
+        kern<<<1, TH, 0, e->stream>>>(a);
+        double v = -1.0;
+        if (cudaMemcpyAsync(&v, e->d_misc.p, 8, cudaMemcpyDeviceToHost, e->stream) == cudaSuccess &&
+            cudaStreamSynchronize(e->stream) == cudaSuccess && v >= 0.0) {
+            slack = (int)((4096u - ((uint32_t)v & 4095u)) & 4095u);
+            cache[(const void *)kern] = slack;
+        }
+    }
+    return slack;
+}
+
+SweepCfg choose_cfg(rr_engine *e)
+{
+    SweepCfg c;
+    // 4 samples per thread (the PTX core of rr_sweep_core.cuh) in 128-thread blocks, 2 blocks per SM:
+    // per-dispatch overhead wants more samples per thread, latency hiding wants more warps, and the
+    // shared-memory tile caps the samples in flight per SM (profiles/r1_config_sweep.txt)
+    const bool big = e->n >= (1 << 15);
+    c.S = e->s_pref ? e->s_pref : (big ? 4 : 1);
+    c.TH = e->th_pref ? e->th_pref : 128;
+    c.occ = e->occ_pref ? e->occ_pref : (c.T() >= 1024 ? 1 : (c.T() >= 512 ? 2 : (c.T() >= 256 ? 3 : 4)));
+    c.slack = std::max(sweep_slack(e, sweep_kernel_for(c, false), c.TH), sweep_slack(e, sweep_kernel_for(c, true), c.TH));
+    // the tile must stage the feature columns a chunk can touch plus a few value slots (cached terms
+    // live in pins first)
+    const int want = std::min(e->d, 24) + 3;
+    while (c.tile_cols() < want && c.occ > 1) --c.occ;
+    while (c.tile_cols() < want && c.S > 1) c.S /= 2;
+    return c;
+}
+
+template <typename T> int upload(rr_engine *e, DevBuf &buf, const T *src, size_t count)
+{
+    const size_t bytes = count * sizeof(T);
+    CU(buf.ensure(std::max<size_t>(bytes, 16)));
+    if (bytes) CU(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += bytes;
+    return RR_OK;
+}
+
 // grid.x of a sweep for a plan with n_chunks chunks
 int sweep_gx(rr_engine *e, const SweepCfg &c, bool special, size_t smem, int n_chunks, int n_tiles)
 {
@@ -315,8 +345,8 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     const int T = cfg.T();
     const int NW = cfg.TH / 32;
     const int n_tiles = (int)((e->n + T - 1) / T);
-    const size_t smem = (size_t)std::max(P.max_tile_cols, 1) * T * 8 + rr::sweep_ring_smem(NW);
-    if (smem > cfg.dyn_smem_budget() + rr::sweep_ring_smem(NW)) return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
+    const size_t smem = (size_t)std::max(P.max_tile_cols, 1) * T * 8 + rr::sweep_ring_smem(NW, cfg.slack);
+    if (smem > cfg.dyn_smem_budget() + rr::sweep_ring_smem(NW, cfg.slack)) return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
     bool special = dd;
     for (const RRIns &x : P.ins)
         if (RR_OP(x.w0) == RI_CLSMET) { special = true; break; }

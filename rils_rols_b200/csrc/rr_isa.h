@@ -34,6 +34,10 @@ static_assert(sizeof(RRIns) == 16, "RRIns must be 16 bytes");
 // neighbourhood: the base solution's terms and the centred target), so that the reductions of a
 // freshly evaluated term against them read no shared memory at all.
 #define RR_NPIN 8
+// The kernel streams a chunk's instructions through shared memory in windows of RR_INS_WINDOW, counted
+// from the chunk's first instruction. USEP and its consumer must sit in the same window (the redirected
+// operand lives in registers that do not survive a window switch): the planner pads with RI_NOP.
+#define RR_INS_WINDOW 64
 
 enum RRInsOp : uint32_t {
     RI_END = 0,
@@ -42,6 +46,7 @@ enum RRInsOp : uint32_t {
     RI_ST,      // tile[w1] = t
     RI_STG,     // out[w1][sample] = t   (materialise a column in global memory)
     RI_LDG,     // t = X[w1][sample]     (engine column straight from global memory, not staged)
+    RI_NOP,     // padding (see RR_INS_WINDOW)
     RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C, RI_RDIV_C,  // t = t op imm / imm op t (R*)
     RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR,  // t = f(t)
     // rarely generated operators share one case: aux = RRRareOp | RB_CONST | RB_SWAP
@@ -49,6 +54,8 @@ enum RRInsOp : uint32_t {
     // Reductions over the samples with a = t: aux bit 0 = t.t, bit 1 = sum(t), aux bits 8-15 = mask
     // of pins to reduce against. Outputs in that order (pins ascending), ids implicit and
     // consecutive from the chunk's dot_base; at most RR_MDOT_MAX_OUT outputs per instruction.
+    // aux bits 16-19 = 1 + j: afterwards pin[j] = t (the planner's "PIN j; MDOT" pair in one dispatch;
+    // j is never in the mask).
     RI_MDOT,
     // double-double reductions (escalation plans): aux bit 0/1 as above, aux bits 8-15 = number of
     // tile-column partners (<= 6, 16-bit column indices packed in w1 and imm); two ids per output

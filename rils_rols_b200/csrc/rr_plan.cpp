@@ -622,6 +622,43 @@ struct BatchPlanner::Chunk {
             const uint64_t hi = (uint64_t)p[2] | ((uint64_t)p[3] << 16) | ((uint64_t)p[4] << 32) | ((uint64_t)p[5] << 48);
             std::memcpy(&x.imm, &hi, 8);
         }
+        // peephole: "PIN j; MDOT" (a fresh term is pinned, then reduced against its partners) becomes one
+        // instruction, the pin riding in aux bits 16-19 of the MDOT: one dispatch less per new term
+        {
+            std::vector<RRIns> out;
+            out.reserve(P.ins.size() - pc_begin);
+            for (size_t i = pc_begin; i < P.ins.size(); ++i) {
+                const RRIns &x = P.ins[i];
+                const uint32_t op = RR_OP(x.w0);
+                if (op >= RI_PIN0 && op < RI_PIN0 + RR_NPIN && i + 1 < P.ins.size() && RR_OP(P.ins[i + 1].w0) == RI_MDOT &&
+                    !(P.ins[i + 1].w0 >> 24) && !((P.ins[i + 1].w0 >> (16 + (op - RI_PIN0))) & 1u)) {
+                    RRIns m = P.ins[i + 1];
+                    m.w0 |= (op - RI_PIN0 + 1u) << 24;
+                    out.push_back(m);
+                    ++i;
+                    continue;
+                }
+                out.push_back(x);
+            }
+            P.ins.resize(pc_begin);
+            P.ins.insert(P.ins.end(), out.begin(), out.end());
+        }
+        // USEP and its consumer stay inside one instruction window (rr_isa.h RR_INS_WINDOW)
+        {
+            std::vector<RRIns> out;
+            out.reserve(P.ins.size() - pc_begin + 16);
+            RRIns nop;
+            std::memset(&nop, 0, sizeof(nop));
+            nop.w0 = RI_NOP;
+            for (size_t i = pc_begin; i < P.ins.size(); ++i) {
+                const uint32_t op = RR_OP(P.ins[i].w0);
+                if (op >= RI_USEP0 && op < RI_USEP0 + RR_NPIN && out.size() % RR_INS_WINDOW == RR_INS_WINDOW - 1)
+                    out.push_back(nop);
+                out.push_back(P.ins[i]);
+            }
+            P.ins.resize(pc_begin);
+            P.ins.insert(P.ins.end(), out.begin(), out.end());
+        }
         RRChunk c;
         std::memset(&c, 0, sizeof(c));
         c.pc_begin = pc_begin;

@@ -32,14 +32,15 @@
 
 namespace rr {
 
-constexpr int kInsWindow = 128;  // instructions per shared-memory window (2 KB), two windows
-// Shared memory of a block besides its tile. Static: instruction windows + mbarriers. Dynamic, in front of
-// the tile: the reduction rings, 4 KB per warp, aligned to 4096 bytes of the shared WINDOW at run time
-// (the PTX core wraps its ring pointer with one LOP3, which needs that alignment; static __align__ is
-// relative to a section that starts 1 KB into the window) — hence up to 4 KB of alignment slack.
-constexpr size_t sweep_static_smem() { return 2 * (kInsWindow + 1) * 16 + 256; }
-constexpr size_t sweep_ring_smem(int warps) { return (size_t)warps * 4096 + 4096; }
-constexpr size_t sweep_fixed_smem(int warps) { return sweep_static_smem() + sweep_ring_smem(warps); }
+constexpr int kInsWindow = RR_INS_WINDOW;  // instructions per shared-memory window (1 KB), two windows
+// Shared memory of a block besides its tile. Static: instruction windows + mbarriers, padded to 3072 bytes
+// so that the dynamic part starts 4096-aligned in the shared WINDOW (1 KB of it is reserved by the
+// system). Dynamic, in front of the tile: the reduction rings, 4 KB per warp, aligned to 4096 bytes of the
+// window at run time (the PTX core wraps its ring pointer with one LOP3, which needs that alignment).
+// The host asks the kernel where its dynamic part starts (n_tiles < 0: probe) and adds the slack.
+constexpr size_t kSweepStaticBytes = 3072;
+constexpr size_t sweep_static_smem() { return kSweepStaticBytes; }
+constexpr size_t sweep_ring_smem(int warps, int slack) { return (size_t)warps * 4096 + (size_t)slack; }
 
 struct SweepArgs {
     const double *X;        // engine matrix: columns (features, y, yc) of `ld` doubles
@@ -52,7 +53,7 @@ struct SweepArgs {
     int64_t acc_stride;
     double *stg;            // RI_STG target: column u at stg + u * ld_stg
     int64_t ld_stg;
-    int32_t n_tiles;
+    int32_t n_tiles;        // < 0: probe, the kernel only reports the shared-window address of its dynamic part in acc[0]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -187,10 +188,16 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     constexpr uint32_t COLB = T * 8u;   // bytes per tile column
     constexpr uint32_t HALFB = T * 4u;  // byte offset of the second half of a column
     extern __shared__ __align__(128) unsigned char rr_dyn[];  // [slack][rings: NW x 16 rows x 32 lanes][tile: columns x T]
-    __shared__ __align__(16) uint4 ibuf[2][kInsWindow + 1];
-    __shared__ __align__(8) uint64_t mbar_tile;
-    __shared__ __align__(8) uint64_t mbar_ins[2];
+    __shared__ __align__(16) unsigned char rr_static[kSweepStaticBytes];
+    static_assert(2 * (kInsWindow + 1) * 16 + 3 * 8 <= kSweepStaticBytes, "static shared memory layout");
+    uint4(*ibuf)[kInsWindow + 1] = reinterpret_cast<uint4(*)[kInsWindow + 1]>(rr_static);
+    uint64_t &mbar_tile = *reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 1) * 16);
+    uint64_t *mbar_ins = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 1) * 16 + 8);
 
+    if (a.n_tiles < 0) {
+        if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.acc[0] = (double)smem_u32(rr_dyn);
+        return;
+    }
     const RRChunk ch = a.chunks[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint4 *prog = reinterpret_cast<const uint4 *>(a.ins + ch.pc_begin);
@@ -359,6 +366,8 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     running = false;
                     pc = kInsWindow;
                     break;
+                case RI_NOP:
+                    break;
                 case RI_LOAD_C:
 #pragma unroll
                     for (int s = 0; s < S; ++s) t[s] = imm;
@@ -501,6 +510,11 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                         for (int s = 0; s < S; ++s)
                             if (!partial || valid[s]) v = fma(t[s], pl[j][s], v);
                         ring_emit(rc, cnt, fl, v);
+                    }
+                    if (w0 >> 24) {  // fused "then pin t"
+                        const int j = (int)((w0 >> 24) - 1u) & (RR_NPIN - 1);
+#pragma unroll
+                        for (int s = 0; s < S; ++s) pl[j][s] = t[s];
                     }
                     break;
                 }

@@ -16,8 +16,9 @@ from rils_rols_b200 import engine as E
 from rils_rols_b200.batch import Batch, rr_batch
 
 RR_NPIN = 8
-(RI_END, RI_WINEND, RI_LOAD_C, RI_ST, RI_STG, RI_LDG, RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C, RI_RDIV_C,
- RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET, RI_PIN0) = range(23)
+(RI_END, RI_WINEND, RI_LOAD_C, RI_ST, RI_STG, RI_LDG, RI_NOP, RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C,
+ RI_RDIV_C, RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET, RI_PIN0) = range(24)
+RR_INS_WINDOW = 64
 RI_LDP0 = RI_PIN0 + RR_NPIN
 RI_USEP0 = RI_LDP0 + RR_NPIN
 RI_FIRST_M = RI_USEP0 + RR_NPIN
@@ -99,7 +100,7 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
             while pc < end:
                 w0, w1, imm = int(plan.ins["w0"][pc]), int(plan.ins["w1"][pc]), float(plan.ins["imm"][pc])
                 pc += 1
-                op, aux = w0 & 0xFF, (w0 >> 8) & 0xFFFF
+                op, aux = w0 & 0xFF, w0 >> 8
                 src = None
                 if op >= RI_FIRST_M:
                     if use_pin >= 0:
@@ -113,6 +114,7 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 use_pin = -1
                 if op == RI_END:
                     break
+                elif op == RI_NOP: pass
                 elif op == RI_LOAD_C: t = np.full(n, imm)
                 elif op == RI_LOAD_M: t = src.copy()
                 elif op == RI_ST:
@@ -140,7 +142,9 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 elif RI_LDP0 <= op < RI_LDP0 + RR_NPIN:
                     assert pins[op - RI_LDP0] is not None, "LDP of an empty pin"
                     t = pins[op - RI_LDP0].copy()
-                elif RI_USEP0 <= op < RI_USEP0 + RR_NPIN: use_pin = op - RI_USEP0
+                elif RI_USEP0 <= op < RI_USEP0 + RR_NPIN:
+                    assert (pc - 1 - int(ch["pc_begin"])) % RR_INS_WINDOW != RR_INS_WINDOW - 1, "USEP at a window end"
+                    use_pin = op - RI_USEP0
                 elif op == RI_SIN: t = np.sin(t)
                 elif op == RI_COS: t = np.cos(t)
                 elif op == RI_LN: t = np.log(t)
@@ -171,6 +175,10 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     for v in vals:
                         dots[out] += v
                         out += 1
+                    if aux >> 16:  # fused "then pin t"
+                        j = (aux >> 16) - 1
+                        assert j < RR_NPIN and not (mask >> j & 1)
+                        pins[j] = t.copy()
                 elif op == RI_MDOTDD:
                     vals = []
                     if aux & 1: vals.append(float(np.dot(t, t)))
