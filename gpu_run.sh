@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python tools/diff_paths.py 40960 > gpurun_out/diff_paths.log 2>&1; grep -v "^   cand" gpurun_out/diff_paths.log | tail -20
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_v6.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
