@@ -34,6 +34,10 @@ static_assert(sizeof(RRIns) == 16, "RRIns must be 16 bytes");
 // neighbourhood: the base solution's terms and the centred target), so that the reductions of a
 // freshly evaluated term against them read no shared memory at all.
 #define RR_NPIN 8
+// ... plus RR_NREG - RR_NPIN *cache registers* of the same kind that PIN / LDP / USEP can address but
+// reductions cannot: the planner parks expensive sub-expressions there that the next few terms share
+// (neighbours of one tree node keep its sibling subtrees: exp(x8)*x9 -> exp(x8)*x3, exp(x8)*sqrt(x9), ...)
+#define RR_NREG 10
 // The kernel streams a chunk's instructions through shared memory in windows of RR_INS_WINDOW, counted
 // from the chunk's first instruction. USEP and its consumer must sit in the same window (the redirected
 // operand lives in registers that do not survive a window switch): the planner pads with RI_NOP.
@@ -62,13 +66,13 @@ enum RRInsOp : uint32_t {
     RI_MDOTDD,
     // classifier metrics of t against y = tile[w1] (rils_rols_cpp.cpp:51-86): three outputs
     RI_CLSMET,
-    // pins: PIN j: pin[j] = t;  LDP j: t = pin[j];  USEP j: the NEXT instruction (a tile-column
+    // value registers j < RR_NREG: PIN j: reg[j] = t;  LDP j: t = reg[j];  USEP j: the NEXT instruction (a tile-column
     // operand form) takes pin[j] as its operand instead of the tile column
     RI_PIN0,
-    RI_LDP0 = RI_PIN0 + RR_NPIN,
-    RI_USEP0 = RI_LDP0 + RR_NPIN,
+    RI_LDP0 = RI_PIN0 + RR_NREG,
+    RI_USEP0 = RI_LDP0 + RR_NREG,
     // ---- forms with a tile-column operand tile[w1]: everything from RI_FIRST_M on ----
-    RI_FIRST_M = RI_USEP0 + RR_NPIN,
+    RI_FIRST_M = RI_USEP0 + RR_NREG,
     RI_LOAD_M = RI_FIRST_M,  // t = tile[w1]
     RI_ADD_M, RI_SUB_M, RI_RSUB_M, RI_MUL_M, RI_DIV_M, RI_RDIV_M,  // t = t op tile[w1] / tile[w1] op t (R*)
     RI_AXPY,    // t = t + imm * tile[w1]  (product rounded, then sum: the c*term + ... chain of

@@ -2,6 +2,7 @@
 #include "rr_plan.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 
@@ -196,6 +197,63 @@ std::string BatchPlanner::analyse(bool no_cse)
             }
         }
     }
+    // expensive inner subtrees shared by several distinct terms (the neighbours of one tree node keep its
+    // sibling subtrees): candidates for the cache registers. Distinct terms are numbered in order of first
+    // appearance, which is the order the planner evaluates them in, so the occurrence lists double as
+    // next-use information.
+    sub_occ_.clear();
+    if (!no_cse) {
+        const double kMinW = 8.0;  // at least a division, a square root or a transcendental inside
+        std::unordered_map<std::string, int32_t> sub_seen;
+        std::vector<std::vector<int32_t>> occ;
+        std::vector<double> wsub;
+        for (size_t u = 0; u < terms_.size(); ++u) {
+            Term &tm = terms_[u];
+            const int32_t root = (int32_t)tm.nodes.size() - 1;
+            wsub.assign(tm.nodes.size(), 0.0);
+            for (int32_t x = 0; x <= root; ++x) {
+                TermNode &nd = tm.nodes[x];
+                if (nd.leaf()) continue;
+                wsub[x] = kW[nd.op] + wsub[nd.left] + (nd.right >= 0 ? wsub[nd.right] : 0.0);
+                if (x == root || wsub[x] < kMinW) continue;
+                key.clear();
+                for (int32_t i = tm.code_begin + nd.first; i <= tm.code_begin + x; ++i) {
+                    const uint32_t w = b_->code[i];
+                    const uint32_t op = RR_INS_OP(w);
+                    key.push_back((char)op);
+                    if (op == RR_OP_CONST) {
+                        char buf[8];
+                        std::memcpy(buf, &b_->consts[RR_INS_ARG(w)], 8);
+                        key.append(buf, 8);
+                    } else if (op == RR_OP_VAR) {
+                        const uint32_t a = RR_INS_ARG(w);
+                        key.append((const char *)&a, 4);
+                    }
+                }
+                auto it = sub_seen.find(key);
+                int32_t id;
+                if (it == sub_seen.end()) {
+                    id = (int32_t)occ.size();
+                    sub_seen.emplace(key, id);
+                    occ.emplace_back();
+                } else {
+                    id = it->second;
+                }
+                nd.sub_id = id;
+                if (occ[id].empty() || occ[id].back() != (int32_t)u) occ[id].push_back((int32_t)u);
+            }
+        }
+        // keep the shared ones only
+        std::vector<int32_t> remap(occ.size(), -1);
+        for (size_t i = 0; i < occ.size(); ++i)
+            if (occ[i].size() >= 2) {
+                remap[i] = (int32_t)sub_occ_.size();
+                sub_occ_.push_back(std::move(occ[i]));
+            }
+        for (Term &tm : terms_)
+            for (TermNode &nd : tm.nodes)
+                if (nd.sub_id >= 0) nd.sub_id = remap[nd.sub_id];
+    }
     // contract weights, SURVEY.md 8(d): W(c) = sum w(op) + k(k+1)/2 + k + (k + 2)
     cand_w_.assign(b_->n_cand, 0.0);
     w_contract_ = 0.0;
@@ -237,6 +295,11 @@ struct BatchPlanner::Chunk {
     int32_t pin_term[RR_NPIN];
     uint64_t pin_stamp[RR_NPIN], pin_hold[RR_NPIN];
     std::unordered_map<int32_t, uint32_t> term_loc;  // resident term -> slot index or PINREF | j
+    // cache registers RR_NPIN.. (rr_isa.h): shared sub-expression held there (-1 free), users in flight
+    int32_t n_cache = 0;
+    int32_t creg_sub[RR_NREG - RR_NPIN];
+    int32_t creg_busy[RR_NREG - RR_NPIN];
+    int32_t cur_term = -1;  // distinct term being generated (next-use horizon of the cache)
     std::vector<std::vector<uint32_t>> mdot_refs;  // pre-patch partner refs of each MDOTDD
     std::vector<size_t> mdot_at;                   // ... and its instruction index
     uint64_t clock = 1, epoch = 1;
@@ -254,6 +317,11 @@ struct BatchPlanner::Chunk {
         }
         pool_cap = std::min(lim.tile_cols - (int32_t)cols.size(), lim.max_slots);
         n_pins = std::min<int32_t>(std::max(pins, 0), RR_NPIN);
+        n_cache = lim.no_cse ? 0 : std::min<int32_t>(std::max(lim.n_cache, 0), RR_NREG - RR_NPIN);
+        for (int r = 0; r < RR_NREG - RR_NPIN; ++r) {
+            creg_sub[r] = -1;
+            creg_busy[r] = 0;
+        }
         for (int j = 0; j < RR_NPIN; ++j) {
             pin_term[j] = -1;
             pin_stamp[j] = pin_hold[j] = 0;
@@ -403,6 +471,7 @@ struct BatchPlanner::Chunk {
         double imm = 0.0;
         bool held = false;       // resident sub-term
         uint64_t saved_hold = 0;
+        int cache_reg = -1;      // shared sub-expression in a cache register
     };
     Operand operand_of(const TermNode &n, bool allow_pin = true)
     {
@@ -424,15 +493,57 @@ struct BatchPlanner::Chunk {
                     slot_pin[o.col] = epoch;
                     slot_stamp[o.col] = clock++;
                 }
+                return o;
+            }
+        }
+        if (n.sub_id >= 0 && allow_pin) {
+            const int r = cached(n.sub_id);
+            if (r >= 0) {
+                o.ok = true;
+                o.cache_reg = r;
+                o.col = PINREF | (uint32_t)(RR_NPIN + r);
+                ++creg_busy[r];
             }
         }
         return o;
     }
     void release(const Operand &o)
     {
+        if (o.cache_reg >= 0) --creg_busy[o.cache_reg];
         if (!o.held) return;
         if (o.col & PINREF) pin_hold[o.col & 0xff] = o.saved_hold;
         else slot_pin[o.col] = o.saved_hold;
+    }
+    int cached(int32_t sub) const
+    {
+        for (int r = 0; r < n_cache; ++r)
+            if (creg_sub[r] == sub) return r;
+        return -1;
+    }
+    // first distinct term after the one being generated that contains `sub` (INT32_MAX: none)
+    int32_t next_use(int32_t sub) const
+    {
+        const std::vector<int32_t> &occ = bp.sub_occurrences(sub);
+        auto it = std::upper_bound(occ.begin(), occ.end(), cur_term);
+        return it == occ.end() ? INT32_MAX : *it;
+    }
+    // t holds shared sub-expression `sub`, just computed: park it in a cache register when it is needed
+    // again sooner than what the register holds now (Belady on the planner's own evaluation order)
+    void maybe_cache(int32_t sub)
+    {
+        if (n_cache == 0 || cached(sub) >= 0) return;
+        const int32_t nu = next_use(sub);
+        if (nu == INT32_MAX) return;
+        int victim = -1;
+        int32_t victim_nu = -1;
+        for (int r = 0; r < n_cache; ++r) {
+            if (creg_busy[r]) continue;
+            const int32_t v = creg_sub[r] < 0 ? INT32_MAX : next_use(creg_sub[r]);
+            if (v > victim_nu) { victim_nu = v; victim = r; }
+        }
+        if (victim < 0 || victim_nu <= nu) return;
+        creg_sub[victim] = sub;
+        emit(RI_PIN0 + RR_NPIN + victim, 0, 0.0, 0);
     }
 
     // leaves t = value(node x)
@@ -446,6 +557,12 @@ struct BatchPlanner::Chunk {
             release(o);
             return;
         }
+        gen_compute(T, x);
+        if (n.sub_id >= 0) maybe_cache(n.sub_id);
+    }
+    void gen_compute(const Term &T, int32_t x)
+    {
+        const TermNode &n = T.nodes[x];
         const int ar = arity(n.op);
         if (ar == 1) {
             gen(T, n.left);
@@ -488,6 +605,7 @@ struct BatchPlanner::Chunk {
     void gen_term(int32_t u)
     {
         const Term &T = bp.term(u);
+        cur_term = u;
         gen(T, (int32_t)T.nodes.size() - 1);
         P.n_term_evals++;
     }
@@ -610,7 +728,7 @@ struct BatchPlanner::Chunk {
             bool has_col = op >= RI_FIRST_M || op == RI_ST || op == RI_CLSMET;
             if (op == RI_RARE) has_col = !(RR_AUX(x.w0) & RB_CONST);
             // the operand of the instruction after USEP comes from the pin: its column field stays 0
-            if (has_col && i > (size_t)pc_begin && RR_OP(P.ins[i - 1].w0) >= RI_USEP0 && RR_OP(P.ins[i - 1].w0) < RI_USEP0 + RR_NPIN)
+            if (has_col && i > (size_t)pc_begin && RR_OP(P.ins[i - 1].w0) >= RI_USEP0 && RR_OP(P.ins[i - 1].w0) < RI_USEP0 + RR_NREG)
                 has_col = false;
             if (has_col) x.w1 = patch(x.w1);
         }
@@ -652,7 +770,7 @@ struct BatchPlanner::Chunk {
             nop.w0 = RI_NOP;
             for (size_t i = pc_begin; i < P.ins.size(); ++i) {
                 const uint32_t op = RR_OP(P.ins[i].w0);
-                if (op >= RI_USEP0 && op < RI_USEP0 + RR_NPIN && out.size() % RR_INS_WINDOW == RR_INS_WINDOW - 1)
+                if (op >= RI_USEP0 && op < RI_USEP0 + RR_NREG && out.size() % RR_INS_WINDOW == RR_INS_WINDOW - 1)
                     out.push_back(nop);
                 out.push_back(P.ins[i]);
             }

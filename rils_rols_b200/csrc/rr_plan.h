@@ -32,6 +32,8 @@ struct TermNode {
     int32_t need = 0;  // Sethi-Ullman spill need
     int32_t first = 0;     // postfix index of the first node of this subtree
     int32_t sub_term = -1; // distinct term whose whole program equals this subtree (subtree-level sharing)
+    int32_t sub_id = -1;   // id of this subtree among the expensive inner subtrees that several distinct terms share
+
     bool leaf() const { return op == RR_OP_CONST || op == RR_OP_VAR; }
 };
 
@@ -60,6 +62,7 @@ struct PlanLimits {
     int32_t max_slots = 1 << 20;  // cap on value slots (cached terms + temporaries) per chunk: bounds the tile
     int32_t target_chunks = 1;
     int32_t n_pins = RR_NPIN;     // pins the Gram plans may use (rr_isa.h); 0 = tile slots only
+    int32_t n_cache = RR_NREG - RR_NPIN;  // cache registers for shared sub-expressions; 0 = off
     bool no_cse = false;
 };
 
@@ -81,6 +84,8 @@ public:
     const Term &term(int32_t u) const { return terms_[u]; }
     double w_contract() const { return w_contract_; }
     const std::vector<double> &cand_contract_w() const { return cand_w_; }
+    // distinct terms (ascending ids) that contain shared sub-expression `sub`
+    const std::vector<int32_t> &sub_occurrences(int32_t sub) const { return sub_occ_[sub]; }
 
     // OLS_FIT, Gram path: Gram + A^T yc + column sums for the candidates in `subset`
     // (nullptr = all). cand_dot: per listed candidate m(m+1)/2 (upper triangle, row-major)
@@ -112,6 +117,7 @@ private:
     std::vector<Term> terms_;
     std::vector<int32_t> term_id_;
     std::vector<double> cand_w_;
+    std::vector<std::vector<int32_t>> sub_occ_;
     double w_contract_ = 0.0;
 
     std::string build_term(int32_t code_begin, int32_t code_len, Term &t) const;

@@ -264,11 +264,11 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         uint32_t cnt = 0, fl = 0;  // reductions emitted / flushed in this chunk and tile
         uint32_t ddcnt = 0;
         // pins: registers of the PTX core (static indices only) or a local array of the generic path
-        double pr[PAIRS ? RR_NPIN * 4 : 1];
-        double pl[RR_NPIN][S];
+        double pr[PAIRS ? RR_NREG * 4 : 1];
+        double pl[RR_NREG][S];
         if constexpr (PAIRS) {
 #pragma unroll
-            for (int i = 0; i < RR_NPIN * 4; ++i) pr[i] = 0.0;
+            for (int i = 0; i < RR_NREG * 4; ++i) pr[i] = 0.0;
         }
         int use_pin = -1;  // generic path: pin redirected into the next tile-column operand
 
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     use_pin = -1;
                 }
                 if (op >= RI_PIN0 && op < RI_FIRST_M) {
-                    const int j = (int)(op - RI_PIN0) & (RR_NPIN - 1);
+                    const int j = (int)((op - RI_PIN0) % RR_NREG);
                     if (op < RI_LDP0) {
 #pragma unroll
                         for (int s = 0; s < S; ++s) pl[j][s] = t[s];
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                         ring_emit(rc, cnt, fl, v);
                     }
                     if (w0 >> 24) {  // fused "then pin t"
-                        const int j = (int)((w0 >> 24) - 1u) & (RR_NPIN - 1);
+                        const int j = (int)(((w0 >> 24) - 1u) % RR_NREG);
 #pragma unroll
                         for (int s = 0; s < S; ++s) pl[j][s] = t[s];
                     }

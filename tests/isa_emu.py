@@ -16,12 +16,13 @@ from rils_rols_b200 import engine as E
 from rils_rols_b200.batch import Batch, rr_batch
 
 RR_NPIN = 8
+RR_NREG = 10
 (RI_END, RI_WINEND, RI_LOAD_C, RI_ST, RI_STG, RI_LDG, RI_NOP, RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C,
  RI_RDIV_C, RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET, RI_PIN0) = range(24)
 RR_INS_WINDOW = 64
-RI_LDP0 = RI_PIN0 + RR_NPIN
-RI_USEP0 = RI_LDP0 + RR_NPIN
-RI_FIRST_M = RI_USEP0 + RR_NPIN
+RI_LDP0 = RI_PIN0 + RR_NREG
+RI_USEP0 = RI_LDP0 + RR_NREG
+RI_FIRST_M = RI_USEP0 + RR_NREG
 (RI_LOAD_M, RI_ADD_M, RI_SUB_M, RI_RSUB_M, RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_AXPY, RI_DOTM) = range(RI_FIRST_M, RI_FIRST_M + 9)
 RR_MDOT_MAX_OUT = 8
 RR_POW, RR_LT, RR_GT, RR_EQ, RR_NE, RR_MIN, RR_MAX = range(7)
@@ -92,7 +93,7 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
             ncols = int(ch["n_cols"])
             tile = {i: cols_global[plan.cols[ch["col_begin"] + i]] for i in range(ncols)}
             t = np.zeros(n)
-            pins = [None] * RR_NPIN
+            pins = [None] * RR_NREG
             use_pin = -1
             out = int(ch["dot_base"])
             pc = int(ch["pc_begin"])
@@ -138,11 +139,11 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 elif op == RI_DOTM:
                     dots[out] += float(np.dot(t, src))
                     out += 1
-                elif RI_PIN0 <= op < RI_PIN0 + RR_NPIN: pins[op - RI_PIN0] = t.copy()
-                elif RI_LDP0 <= op < RI_LDP0 + RR_NPIN:
+                elif RI_PIN0 <= op < RI_PIN0 + RR_NREG: pins[op - RI_PIN0] = t.copy()
+                elif RI_LDP0 <= op < RI_LDP0 + RR_NREG:
                     assert pins[op - RI_LDP0] is not None, "LDP of an empty pin"
                     t = pins[op - RI_LDP0].copy()
-                elif RI_USEP0 <= op < RI_USEP0 + RR_NPIN:
+                elif RI_USEP0 <= op < RI_USEP0 + RR_NREG:
                     assert (pc - 1 - int(ch["pc_begin"])) % RR_INS_WINDOW != RR_INS_WINDOW - 1, "USEP at a window end"
                     use_pin = op - RI_USEP0
                 elif op == RI_SIN: t = np.sin(t)
@@ -177,7 +178,7 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                         out += 1
                     if aux >> 16:  # fused "then pin t"
                         j = (aux >> 16) - 1
-                        assert j < RR_NPIN and not (mask >> j & 1)
+                        assert j < RR_NREG and not (mask >> j & 1)
                         pins[j] = t.copy()
                 elif op == RI_MDOTDD:
                     vals = []
