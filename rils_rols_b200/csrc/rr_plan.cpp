@@ -1023,8 +1023,11 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
     const int32_t need = max_need(*this, units);
     int32_t widest = 0;
     for (const Unit &u : units) widest = std::max(widest, (int32_t)u.terms.size());
-    // all terms resident when they fit; wide candidates stream their terms instead (below)
-    const int32_t min_slots = std::min(widest + need + 2, std::max(need + 4, lim.tile_cols / 2));
+    const int32_t pins = std::min<int32_t>(std::max(lim.n_pins, 0), RR_NPIN);
+    // all terms resident (pins first, then tile slots) when they fit; wide candidates stream their terms
+    // instead (below)
+    const int32_t min_slots = pins > 1 ? need + 2
+                                       : std::min(widest + need + 2, std::max(need + 4, lim.tile_cols / 2));
     std::vector<ChunkSpec> specs;
     std::string err = cut_chunks(*this, units, lim, {cols.y}, min_slots, specs);
     if (!err.empty()) return err + " (residual pass)";
@@ -1033,7 +1036,7 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
     std::vector<uint32_t> partners;
     std::vector<int32_t> ids;
     for (const ChunkSpec &cs : specs) {
-        Chunk ch(*this, P, lim, cs.cols, 0);
+        Chunk ch(*this, P, lim, cs.cols, pins);
         const uint32_t y_col = ch.staged(cols.y);
         for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
             const int32_t c = subset[ui];
@@ -1041,8 +1044,8 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
             const int32_t m = (int32_t)T.size();
             const double *cf = coef + b_->cand_term_begin[c] + c;
             ch.unpin_all();
-            if (m + need + 2 > ch.pool_cap) {
-                // wide candidate: not all terms fit the tile at once. Stream them: yhat accumulates in one
+            if (m + need + 2 > ch.pool_cap + ch.free_pins()) {
+                // wide candidate: not all terms fit at once. Stream them: yhat accumulates in one
                 // slot in the reference's association order, then every term is evaluated a second time
                 // against the residual.
                 const int32_t acc = ch.alloc_slot(-2);
@@ -1077,24 +1080,25 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
                 ch.free_slot(acc);
                 continue;
             }
-            std::vector<uint32_t> slot(m);
+            std::vector<uint32_t> loc(m);
             for (int32_t i = 0; i < m; ++i) {
-                slot[i] = ch.ensure(T[i]);
+                loc[i] = ch.ensure(T[i]);
                 if (!ch.err.empty()) return ch.err;
             }
+            // a candidate may list one distinct term twice: reduce against each location once
             // yhat in the association order of rils_rols_cpp.cpp:488-515
             bool first = true;
             for (int32_t i = 0; i < m; ++i) {
                 const double ci = cf[i];
                 if (ci == 0.0) continue;  // snapped away (value_zero)
                 if (first) {
-                    ch.emit(RI_LOAD_M, (uint32_t)slot[i], 0.0, 0);
+                    ch.emit_load(loc[i]);
                     if (ci != 1.0) ch.emit(RI_MUL_C, 0, ci, 1);
                     first = false;
                 } else if (ci == 1.0) {
-                    ch.emit(RI_ADD_M, (uint32_t)slot[i], 0.0, 1);
+                    ch.emit_m(RI_ADD_M, loc[i], 0.0, 1);
                 } else {
-                    ch.emit(RI_AXPY, (uint32_t)slot[i], ci, 2);
+                    ch.emit_m(RI_AXPY, loc[i], ci, 2);
                 }
             }
             if (cf[m] != 0.0) {
@@ -1104,12 +1108,22 @@ std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &col
             }
             if (first) ch.emit(RI_LOAD_C, 0, 0.0, 0);
             ch.emit(RI_RSUB_M, y_col, 0.0, 1);  // t = y - yhat
+            // r.r, r.1, r.t_i; a distinct term listed twice is reduced once
             partners.clear();
-            for (int32_t i = 0; i < m; ++i) partners.push_back((uint32_t)slot[i]);
+            std::vector<int32_t> ppos(m, -1);
+            for (int32_t i = 0; i < m; ++i) {
+                for (int32_t j = 0; j < i; ++j)
+                    if (loc[j] == loc[i]) { ppos[i] = ppos[j]; break; }
+                if (ppos[i] < 0) {
+                    ppos[i] = (int32_t)partners.size();
+                    partners.push_back(loc[i]);
+                }
+            }
             ids.clear();
-            ch.mdot(true, true, partners, false, ids);  // r.r, r.1, r.t_i
+            ch.mdot(true, true, partners, false, ids);
+            if (!ch.err.empty()) return ch.err;
             cand_dot.push_back(ids[0]);
-            for (int32_t i = 0; i < m; ++i) cand_dot.push_back(ids[2 + i]);
+            for (int32_t i = 0; i < m; ++i) cand_dot.push_back(ids[2 + ppos[i]]);
             cand_dot.push_back(ids[1]);
             cand_dot_begin.push_back((int32_t)cand_dot.size());
         }
