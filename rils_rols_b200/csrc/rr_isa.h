@@ -25,7 +25,7 @@
 struct RRIns {
     uint32_t w0;  // opcode | aux << 8
     uint32_t w1;  // tile column index (operand / destination); 0 when unused
-    double imm;   // constant operand / AXPY coefficient / packed MDOTDD partners
+    double imm;   // constant operand / AXPY coefficient
 };
 static_assert(sizeof(RRIns) == 16, "RRIns must be 16 bytes");
 
@@ -61,8 +61,8 @@ enum RRInsOp : uint32_t {
     // aux bits 16-19 = 1 + j: afterwards pin[j] = t (the planner's "PIN j; MDOT" pair in one dispatch;
     // j is never in the mask).
     RI_MDOT,
-    // double-double reductions (escalation plans): aux bit 0/1 as above, aux bits 8-15 = number of
-    // tile-column partners (<= 6, 16-bit column indices packed in w1 and imm); two ids per output
+    // double-double reductions (escalation plans): same encoding as RI_MDOT, each output accumulated in
+    // double-double and taking two ids (hi, lo)
     RI_MDOTDD,
     // classifier metrics of t against y = tile[w1] (rils_rols_cpp.cpp:51-86): three outputs
     RI_CLSMET,
@@ -78,6 +78,7 @@ enum RRInsOp : uint32_t {
     RI_AXPY,    // t = t + imm * tile[w1]  (product rounded, then sum: the c*term + ... chain of
                 //                          rils_rols_cpp.cpp:503-510)
     RI_DOTM,    // one reduction: t . tile[w1]
+    RI_DOTMDD,  // the same in double-double (two ids)
     RI_OPCOUNT
 };
 
@@ -87,13 +88,12 @@ enum : uint32_t {
     RB_SWAP = 1u << 5,   // t = src op t
     MD_SELF = 1u << 0,
     MD_ONE = 1u << 1,
-    MD_MAX_PARTNERS = 6,  // MDOTDD tile-column partners per instruction
     RR_MDOT_MAX_OUT = 8,  // outputs of one RI_MDOT (the kernel's reduction ring drains in groups of 8)
 };
 #define RR_W0(op, aux) ((uint32_t)(op) | ((uint32_t)(aux) << 8))
 #define RR_OP(w0) ((w0) & 0xffu)
 #define RR_AUX(w0) ((w0) >> 8)
-#define RR_MDOT_COUNT(w0) (((w0) >> 16) & 0xffu)  /* MDOTDD partner count / MDOT pin mask */
+#define RR_MDOT_MASK(w0) (((w0) >> 16) & 0xffu)  /* pins to reduce against */
 
 // One independently schedulable piece of a sweep: its own staged columns, slot state and
 // dot range. Large-n sweeps use one chunk (maximal sharing); small-n sweeps are cut into

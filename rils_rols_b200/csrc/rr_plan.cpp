@@ -300,8 +300,6 @@ struct BatchPlanner::Chunk {
     int32_t creg_sub[RR_NREG - RR_NPIN];
     int32_t creg_busy[RR_NREG - RR_NPIN];
     int32_t cur_term = -1;  // distinct term being generated (next-use horizon of the cache)
-    std::vector<std::vector<uint32_t>> mdot_refs;  // pre-patch partner refs of each MDOTDD
-    std::vector<size_t> mdot_at;                   // ... and its instruction index
     uint64_t clock = 1, epoch = 1;
     std::string err;
 
@@ -639,33 +637,8 @@ struct BatchPlanner::Chunk {
     // partner order); dd outputs take two ids each and accept tile columns only.
     void mdot(bool self, bool one, const std::vector<uint32_t> &partners, bool dd, std::vector<int32_t> &ids)
     {
-        if (dd) {
-            size_t done = 0;
-            bool first = true;
-            do {
-                const size_t take = std::min<size_t>(MD_MAX_PARTNERS, partners.size() - done);
-                uint32_t aux = 0;
-                int n_out = (int)take;
-                if (first && self) { aux |= MD_SELF; ++n_out; }
-                if (first && one) { aux |= MD_ONE; ++n_out; }
-                aux |= (uint32_t)take << 8;
-                if (n_out > 0) {
-                    for (size_t j = done; j < done + take; ++j)
-                        if (partners[j] & PINREF) { err = "internal: pinned partner in a double-double plan"; return; }
-                    mdot_at.push_back(P.ins.size());
-                    mdot_refs.emplace_back(partners.begin() + done, partners.begin() + done + take);
-                    emit(RR_W0(RI_MDOTDD, aux), 0, 0.0, 10.0 * n_out);
-                    for (int i = 0; i < n_out; ++i) {
-                        ids.push_back(P.n_dots);
-                        P.n_dots += 2;
-                    }
-                    P.n_dot_ins += n_out;
-                }
-                done += take;
-                first = false;
-            } while (done < partners.size());
-            return;
-        }
+        const int step = dd ? 2 : 1;
+        const double wdot = dd ? 10.0 : 1.0;
         // pinned partners ride in the mask of RI_MDOT (outputs: self, one, pins ascending; at most
         // RR_MDOT_MAX_OUT per instruction); every other partner is one RI_DOTM
         const size_t id0 = ids.size();
@@ -694,8 +667,11 @@ struct BatchPlanner::Chunk {
                     ++n_out;
                 }
             if (n_out == 0) break;
-            emit(RR_W0(RI_MDOT, aux), 0, 0.0, 1.0 * n_out);
-            for (size_t q : slots_out) ids[q] = P.n_dots++;
+            emit(RR_W0(dd ? RI_MDOTDD : RI_MDOT, aux), 0, 0.0, wdot * n_out);
+            for (size_t q : slots_out) {
+                ids[q] = P.n_dots;
+                P.n_dots += step;
+            }
             P.n_dot_ins += n_out;
             bool more = false;
             for (int jj = j; jj < RR_NPIN; ++jj) more = more || pin_pos[jj] >= 0;
@@ -703,8 +679,9 @@ struct BatchPlanner::Chunk {
         }
         for (size_t i = 0; i < partners.size(); ++i)
             if (!(partners[i] & PINREF)) {
-                emit(RI_DOTM, partners[i], 0.0, 1.0);
-                ids[part0 + i] = P.n_dots++;
+                emit(dd ? RI_DOTMDD : RI_DOTM, partners[i], 0.0, wdot);
+                ids[part0 + i] = P.n_dots;
+                P.n_dots += step;
                 P.n_dot_ins += 1;
             }
     }
@@ -732,14 +709,6 @@ struct BatchPlanner::Chunk {
                 has_col = false;
             if (has_col) x.w1 = patch(x.w1);
         }
-        for (size_t k = 0; k < mdot_at.size(); ++k) {
-            RRIns &x = P.ins[mdot_at[k]];
-            uint16_t p[MD_MAX_PARTNERS] = {0, 0, 0, 0, 0, 0};
-            for (size_t j = 0; j < mdot_refs[k].size(); ++j) p[j] = (uint16_t)patch(mdot_refs[k][j]);
-            x.w1 = (uint32_t)p[0] | ((uint32_t)p[1] << 16);
-            const uint64_t hi = (uint64_t)p[2] | ((uint64_t)p[3] << 16) | ((uint64_t)p[4] << 32) | ((uint64_t)p[5] << 48);
-            std::memcpy(&x.imm, &hi, 8);
-        }
         // peephole: "PIN j; MDOT" (a fresh term is pinned, then reduced against its partners) becomes one
         // instruction, the pin riding in aux bits 16-19 of the MDOT: one dispatch less per new term
         {
@@ -748,7 +717,8 @@ struct BatchPlanner::Chunk {
             for (size_t i = pc_begin; i < P.ins.size(); ++i) {
                 const RRIns &x = P.ins[i];
                 const uint32_t op = RR_OP(x.w0);
-                if (op >= RI_PIN0 && op < RI_PIN0 + RR_NPIN && i + 1 < P.ins.size() && RR_OP(P.ins[i + 1].w0) == RI_MDOT &&
+                if (op >= RI_PIN0 && op < RI_PIN0 + RR_NPIN && i + 1 < P.ins.size() &&
+                    (RR_OP(P.ins[i + 1].w0) == RI_MDOT || RR_OP(P.ins[i + 1].w0) == RI_MDOTDD) &&
                     !(P.ins[i + 1].w0 >> 24) && !((P.ins[i + 1].w0 >> (16 + (op - RI_PIN0))) & 1u)) {
                     RRIns m = P.ins[i + 1];
                     m.w0 |= (op - RI_PIN0 + 1u) << 24;
@@ -889,9 +859,9 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
         units[i].w = cand_w_[c];
     }
     const int32_t need = max_need(*this, units);
-    // double-double reductions read tile columns only; otherwise cached terms and the centred target
-    // live in pins and the tile only holds the spill temporaries and the overflow
-    const int32_t pins = dd ? 0 : std::min<int32_t>(std::max(lim.n_pins, 0), RR_NPIN);
+    // cached terms and the centred target live in pins; the tile only holds the spill temporaries and
+    // the overflow
+    const int32_t pins = std::min<int32_t>(std::max(lim.n_pins, 0), RR_NPIN);
     // slots wanted: all terms of the widest candidate resident + spill temporaries; if the tile
     // cannot give that, pairs are scheduled in blocks (see below)
     const int32_t min_slots = pins > 1 ? need + 1 + (pins < 4 ? 3 : 0)

@@ -518,28 +518,26 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     }
                     break;
                 }
-                case RI_MDOTDD: if constexpr (SPECIAL) {
-                    // a double-double plan holds MDOTDD reductions only (rr_plan.cpp): they bypass the
+                case RI_MDOTDD:
+                case RI_DOTMDD: if constexpr (SPECIAL) {
+                    // a double-double plan holds double-double reductions only (rr_plan.cpp): they bypass the
                     // ring; output i occupies the (hi, lo) pair at 2i in the warp's private row
-                    const uint32_t np = (w0 >> 16) & 0xffu;
-                    const int has_self = (w0 >> 8) & 1, has_one = (w0 >> 9) & 1;
-                    const int n_out = (int)np + has_self + has_one;
-                    uint32_t q0 = w1, q1 = in.z, q2 = in.w;
+                    const bool single = op == RI_DOTMDD;
+                    const uint32_t mask = single ? 0u : (w0 >> 16) & 0xffu;
+                    const int has_self = single ? 0 : (w0 >> 8) & 1, has_one = single ? 0 : (w0 >> 9) & 1;
 #pragma unroll 1
-                    for (int o = 0; o < n_out; ++o) {
-                        int kind = 2;  // 0 self, 1 one, 2 column
-                        if (has_self && o == 0) kind = 0;
-                        else if (has_one && o == has_self) kind = 1;
-                        const uint32_t p = tile_sh + (q0 & 0xffffu) * COLB;
-                        if (kind == 2) {
-                            q0 = __funnelshift_r(q0, q1, 16);
-                            q1 = __funnelshift_r(q1, q2, 16);
-                            q2 >>= 16;
-                        }
+                    for (int o = -2; o <= RR_NPIN; ++o) {  // -2 self, -1 one, 0..7 pins, RR_NPIN: the tile column of DOTMDD
+                        if (o == -2 && !has_self) continue;
+                        if (o == -1 && !has_one) continue;
+                        if (o >= 0 && o < RR_NPIN && !((mask >> o) & 1u)) continue;
+                        if (o == RR_NPIN && !single) continue;
                         double hi = 0.0, lo = 0.0;
 #pragma unroll
-                        for (int s = 0; s < S; ++s)
-                            if (valid[s]) dd_add_prod(hi, lo, t[s], kind == 0 ? t[s] : (kind == 1 ? 1.0 : lds_f64(p + soff(s))));
+                        for (int s = 0; s < S; ++s) {
+                            if (!valid[s]) continue;
+                            const double v = o == -2 ? t[s] : (o == -1 ? 1.0 : (o == RR_NPIN ? u[s] : pl[o & (RR_NPIN - 1)][s]));
+                            dd_add_prod(hi, lo, t[s], v);
+                        }
 #pragma unroll
                         for (int m = 16; m > 0; m >>= 1) {
                             const double h2 = __shfl_xor_sync(0xffffffffu, hi, m);
@@ -555,6 +553,11 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                             q[1] = al;
                         }
                         ++ddcnt;
+                    }
+                    if (!single && (w0 >> 24)) {  // fused "then pin t"
+                        const int j = (int)(((w0 >> 24) - 1u) % RR_NREG);
+#pragma unroll
+                        for (int s = 0; s < S; ++s) pl[j][s] = t[s];
                     }
                     break;
                 }

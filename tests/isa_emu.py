@@ -23,7 +23,8 @@ RR_INS_WINDOW = 64
 RI_LDP0 = RI_PIN0 + RR_NREG
 RI_USEP0 = RI_LDP0 + RR_NREG
 RI_FIRST_M = RI_USEP0 + RR_NREG
-(RI_LOAD_M, RI_ADD_M, RI_SUB_M, RI_RSUB_M, RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_AXPY, RI_DOTM) = range(RI_FIRST_M, RI_FIRST_M + 9)
+(RI_LOAD_M, RI_ADD_M, RI_SUB_M, RI_RSUB_M, RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_AXPY, RI_DOTM,
+ RI_DOTMDD) = range(RI_FIRST_M, RI_FIRST_M + 10)
 RR_MDOT_MAX_OUT = 8
 RR_POW, RR_LT, RR_GT, RR_EQ, RR_NE, RR_MIN, RR_MAX = range(7)
 RB_CONST, RB_SWAP = 1 << 4, 1 << 5
@@ -136,9 +137,9 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 elif op == RI_RDIV_C: t = imm / t
                 elif op == RI_RDIV_M: t = src / t
                 elif op == RI_AXPY: t = t + imm * src
-                elif op == RI_DOTM:
+                elif op in (RI_DOTM, RI_DOTMDD):
                     dots[out] += float(np.dot(t, src))
-                    out += 1
+                    out += 2 if op == RI_DOTMDD else 1
                 elif RI_PIN0 <= op < RI_PIN0 + RR_NREG: pins[op - RI_PIN0] = t.copy()
                 elif RI_LDP0 <= op < RI_LDP0 + RR_NREG:
                     assert pins[op - RI_LDP0] is not None, "LDP of an empty pin"
@@ -163,7 +164,8 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     elif r == RR_NE: t = (x != v).astype(float)
                     elif r == RR_MIN: t = np.where(x < v, x, v)
                     else: t = np.where(x > v, x, v)
-                elif op == RI_MDOT:
+                elif op in (RI_MDOT, RI_MDOTDD):
+                    step = 2 if op == RI_MDOTDD else 1
                     vals = []
                     if aux & 1: vals.append(float(np.dot(t, t)))
                     if aux & 2: vals.append(float(np.sum(t)))
@@ -175,23 +177,11 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     assert 0 < len(vals) <= RR_MDOT_MAX_OUT
                     for v in vals:
                         dots[out] += v
-                        out += 1
+                        out += step
                     if aux >> 16:  # fused "then pin t"
                         j = (aux >> 16) - 1
                         assert j < RR_NREG and not (mask >> j & 1)
                         pins[j] = t.copy()
-                elif op == RI_MDOTDD:
-                    vals = []
-                    if aux & 1: vals.append(float(np.dot(t, t)))
-                    if aux & 2: vals.append(float(np.sum(t)))
-                    npart = (aux >> 8) & 0xFF
-                    packed = w1 | (int(np.float64(imm).view(np.uint64)) << 32)
-                    for j in range(npart):
-                        c = (packed >> (16 * j)) & 0xFFFF
-                        vals.append(float(np.dot(t, tile[c])))
-                    for v in vals:
-                        dots[out] += v
-                        out += 2
                 elif op == RI_CLSMET:
                     y = tile[w1]
                     ypb, yb = (t >= 0.5).astype(float), (y >= 0.5).astype(float)
