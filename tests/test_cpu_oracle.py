@@ -6,12 +6,16 @@
   exists: the build container; skipped on the GPU box);
 * the edge cases of node::evaluate_inner / fitness() the kernels must reproduce.
 """
+import os
+
 import numpy as np
 import pytest
 
 from oracle import pyoracle as O
 from rils_rols_b200 import batch as B
 from rils_rols_b200 import workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CONFIGS = ["cfg1_toy", "cfg2_diabetes", "cfg3_breast_cancer"]
 REF_KEYS = ("ref_coef", "ref_nonzero_pivots", "ref_f0", "ref_f1", "ref_size")
@@ -163,3 +167,18 @@ def test_ols_snapping_and_size_rules():
     b2 = B.Batch(B.MODE_OLS_FIT, [0, 0], [0], np.zeros(0, dtype=np.uint32), np.zeros(0))
     r2, g0, g1, gs = O.score_batch(O.feature_major(X), y, b2)
     assert abs(r2.coef[0] - y.mean()) < 1e-12 and gs[0] == 1 and abs(g0[0] - 1.0) < 1e-12
+
+
+def test_fast_transcendentals_within_one_ulp(tmp_path):
+    """oracle/rr_fastmath_check.c restates the PTX fast paths of sin/cos/exp/log operation by operation and
+    measures them against glibc: every result within 1 ulp of the correctly rounded value."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = os.path.join(ROOT, "oracle", "rr_fastmath_check.c")
+    exe = str(tmp_path / "fm")
+    subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-o", exe, src, "-lm"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
