@@ -73,6 +73,26 @@ __device__ inline void gather_gram(const double *dots, const int32_t *idx, int m
     b[m] = k.sum_yc;
 }
 
+// Columns that take part in the factorisation: all but the LATER copies of a term that a candidate lists
+// twice (neighbours that rebuild an existing term do). The planner reduces each distinct (term, term) pair
+// once, so copies share their reduction ids and their Gram rows are bit-identical: the second copy's
+// updated norm is exactly zero after the first has been eliminated, column-pivoted QR drops it
+// (ColPivHouseholderQR.h:517-527: the larger index loses the tie and ends below the threshold) and its
+// coefficient is 0. Deciding that from the ids instead of from rounding noise keeps such candidates out
+// of the double-double escalation. amap: alive column indices, the free term (index m) last.
+__device__ inline int alive_columns(const int32_t *idx, int m, int *amap)
+{
+    int na = 0;
+    for (int j = 0; j < m; ++j) {
+        const int32_t dj = idx[j * m - j * (j - 1) / 2];  // id of t_j . t_j in the row-major upper triangle
+        bool dup = false;
+        for (int i = 0; i < j && !dup; ++i) dup = idx[i * m - i * (i - 1) / 2] == dj;
+        if (!dup) amap[na++] = j;
+    }
+    amap[na++] = m;
+    return na;
+}
+
 // In-place diagonal-pivoted Cholesky of the symmetric W (kk x kk, both triangles valid on entry;
 // on exit the lower triangle of the leading rank x rank block holds L in pivoted order).
 // Returns the numerical rank by the reference's rule; rho_min = min over pivots of
@@ -213,10 +233,19 @@ __global__ void rr_gram_solve(const GramArgs a)
         a.status[c] = ST_DONE;
         return;
     }
-    for (int i = 0; i < kk * kk; ++i) W[i] = G[i];
+    // workspace tail (4.5 kk doubles are free behind perm): alive map, compacted right-hand side and solution
+    int *amap = perm + kk;
+    double *rhs2 = reinterpret_cast<double *>(amap + kk), *x2 = rhs2 + kk;
+    const int na = alive_columns(idx, m, amap);
+    for (int p = 0; p < na; ++p) {
+        for (int q = 0; q < na; ++q) W[p * na + q] = G[amap[p] * kk + amap[q]];
+        rhs2[p] = rhs[amap[p]];
+    }
     double rho_min;
-    const int rank = pivoted_cholesky(W, kk, kk, perm, orig, a.k.n_total, &rho_min);
-    cholesky_solve(W, kk, kk, rank, perm, rhs, z, x);
+    const int rank = pivoted_cholesky(W, na, na, perm, orig, a.k.n_total, &rho_min);
+    cholesky_solve(W, na, na, rank, perm, rhs2, z, x2);
+    for (int i = 0; i < kk; ++i) x[i] = 0.0;
+    for (int p = 0; p < na; ++p) x[amap[p]] = x2[p];
 
     uint32_t flags = rank < kk ? RR_RES_RANKDEF : 0u, status = ST_DONE;
     double cmax = 0.0;
@@ -278,10 +307,15 @@ __global__ void rr_refine_update(const RefineArgs a)
     double *cs = a.g.coef_snapped + a.g.cand_term_begin[c] + c;
     const int32_t *ridx = a.rcand_dot + a.rcand_dot_begin[li];
 
-    gather_gram(a.g.dots, a.g.cand_dot + a.g.cand_dot_begin[li], m, a.g.k, G, kk, b);
-    for (int i = 0; i < kk * kk; ++i) W[i] = G[i];
+    const int32_t *idx = a.g.cand_dot + a.g.cand_dot_begin[li];
+    gather_gram(a.g.dots, idx, m, a.g.k, G, kk, b);
+    int *amap = perm + kk;
+    double *g2 = reinterpret_cast<double *>(amap + kk), *x2 = g2 + kk;
+    const int na = alive_columns(idx, m, amap);  // see rr_gram_solve
+    for (int p = 0; p < na; ++p)
+        for (int q = 0; q < na; ++q) W[p * na + q] = G[amap[p] * kk + amap[q]];
     double rho_min;
-    const int rank = pivoted_cholesky(W, kk, kk, perm, orig, a.g.k.n_total, &rho_min);
+    const int rank = pivoted_cholesky(W, na, na, perm, orig, a.g.k.n_total, &rho_min);
     const double ssr0 = a.rdots[ridx[0]];
     double *g = b;  // reuse: g = A^T r0
     for (int i = 0; i < m; ++i) g[i] = a.rdots[ridx[1 + i]];
@@ -292,7 +326,10 @@ __global__ void rr_refine_update(const RefineArgs a)
         a.delta_rel[c] = 0.0;
         return;
     }
-    cholesky_solve(W, kk, kk, rank, perm, g, z, x);  // x = delta
+    for (int p = 0; p < na; ++p) g2[p] = g[amap[p]];
+    cholesky_solve(W, na, na, rank, perm, g2, z, x2);  // delta on the alive columns
+    for (int i = 0; i < kk; ++i) x[i] = 0.0;
+    for (int p = 0; p < na; ++p) x[amap[p]] = x2[p];
     double dmax = 0.0, cmax = 0.0;
     for (int i = 0; i < kk; ++i) {
         const double c1 = cs[i] + x[i];
