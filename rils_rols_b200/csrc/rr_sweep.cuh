@@ -263,6 +263,11 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         for (int s = 0; s < S; ++s) t[s] = 0.0;
         uint32_t cnt = 0, fl = 0;  // reductions emitted / flushed in this chunk and tile
         uint32_t ddcnt = 0;
+        double2 dd_next = make_double2(0.0, 0.0);  // running (hi, lo) of double-double output `ddcnt`, prefetched
+        if constexpr (SPECIAL) {
+            // double-double plans have even dot ids throughout (pairs); classifier-metric plans do not use this
+            if ((reinterpret_cast<uintptr_t>(rc.acc_row) & 15u) == 0) dd_next = __ldcg(reinterpret_cast<const double2 *>(rc.acc_row));
+        }
         // pins: registers of the PTX core (static indices only) or a local array of the generic path
         double pr[PAIRS ? RR_NREG * 4 : 1];
         double pl[RR_NREG][S];
@@ -544,13 +549,15 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                             const double l2_ = __shfl_xor_sync(0xffffffffu, lo, m);
                             dd_add(hi, lo, h2, l2_);
                         }
-                        // one writer per (hi, lo) pair of the warp's row
-                        if (lane == 0) {
+                        // one writer per (hi, lo) pair of the warp's row; the running pair was fetched while
+                        // the previous output was being reduced (an L2 round trip per output otherwise), and
+                        // the next one is requested now (rows are padded: reading one pair past the end is safe)
+                        {
                             double *q = rc.acc_row + 2u * ddcnt;
-                            double ah = q[0], al = q[1];
+                            double ah = dd_next.x, al = dd_next.y;
+                            dd_next = __ldcg(reinterpret_cast<const double2 *>(q + 2));
                             dd_add(ah, al, hi, lo);
-                            q[0] = ah;
-                            q[1] = al;
+                            if (lane == 0) *reinterpret_cast<double2 *>(q) = make_double2(ah, al);
                         }
                         ++ddcnt;
                     }
