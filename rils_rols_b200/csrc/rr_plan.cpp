@@ -202,10 +202,12 @@ std::string BatchPlanner::analyse(bool no_cse)
     // appearance, which is the order the planner evaluates them in, so the occurrence lists double as
     // next-use information.
     sub_occ_.clear();
+    sub_size_.clear();
     if (!no_cse) {
         const double kMinW = 8.0;  // at least a division, a square root or a transcendental inside
         std::unordered_map<std::string, int32_t> sub_seen;
         std::vector<std::vector<int32_t>> occ;
+        std::vector<int32_t> osize;
         std::vector<double> wsub;
         for (size_t u = 0; u < terms_.size(); ++u) {
             Term &tm = terms_[u];
@@ -236,6 +238,7 @@ std::string BatchPlanner::analyse(bool no_cse)
                     id = (int32_t)occ.size();
                     sub_seen.emplace(key, id);
                     occ.emplace_back();
+                    osize.push_back(x - nd.first + 1);
                 } else {
                     id = it->second;
                 }
@@ -249,6 +252,7 @@ std::string BatchPlanner::analyse(bool no_cse)
             if (occ[i].size() >= 2) {
                 remap[i] = (int32_t)sub_occ_.size();
                 sub_occ_.push_back(std::move(occ[i]));
+                sub_size_.push_back(osize[i]);
             }
         for (Term &tm : terms_)
             for (TermNode &nd : tm.nodes)
@@ -532,14 +536,18 @@ struct BatchPlanner::Chunk {
         if (n_cache == 0 || cached(sub) >= 0) return;
         const int32_t nu = next_use(sub);
         if (nu == INT32_MAX) return;
+        // victim: farthest next use; among equals the smaller sub-expression (an enclosing one that is
+        // needed just as soon makes the enclosed one redundant: the hit happens at the outer node)
         int victim = -1;
-        int32_t victim_nu = -1;
+        int32_t victim_nu = -1, victim_size = 0;
         for (int r = 0; r < n_cache; ++r) {
             if (creg_busy[r]) continue;
             const int32_t v = creg_sub[r] < 0 ? INT32_MAX : next_use(creg_sub[r]);
-            if (v > victim_nu) { victim_nu = v; victim = r; }
+            const int32_t sz = creg_sub[r] < 0 ? 0 : bp.sub_size(creg_sub[r]);
+            if (v > victim_nu || (v == victim_nu && sz < victim_size)) { victim_nu = v; victim_size = sz; victim = r; }
         }
-        if (victim < 0 || victim_nu <= nu) return;
+        if (victim < 0) return;
+        if (victim_nu < nu || (victim_nu == nu && victim_size >= bp.sub_size(sub))) return;
         creg_sub[victim] = sub;
         emit(RI_PIN0 + RR_NPIN + victim, 0, 0.0, 0);
     }
@@ -858,6 +866,11 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
             units[i].terms.push_back(term_id_[t]);
         units[i].w = cand_w_[c];
     }
+    // units (ascending) that list each distinct term: look-ahead for "is this term used again soon"
+    std::vector<std::vector<int32_t>> term_units(terms_.size());
+    for (size_t i = 0; i < units.size(); ++i)
+        for (int32_t t : units[i].terms)
+            if (term_units[t].empty() || term_units[t].back() != (int32_t)i) term_units[t].push_back((int32_t)i);
     const int32_t need = max_need(*this, units);
     // cached terms and the centred target live in pins; the tile only holds the spill temporaries and
     // the overflow
@@ -906,8 +919,10 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
             ch.unpin_all();
             const int32_t room = ch.free_pins() + ch.pool_cap - (need + 1);
             if (room < 2) return "tile too small";
-            // t = u; reductions of u with itself, ones, yc and every partner already resident
-            auto reduce_term = [&](int32_t u, const std::vector<int32_t> &done) {
+            // t = u; reductions of u with itself, ones, yc and every partner already resident.
+            // transient: u is the last term reduced for this candidate and no candidate close by lists it
+            // again, so it is evaluated into t and never stored (one instruction less per new term)
+            auto reduce_term = [&](int32_t u, const std::vector<int32_t> &done, bool transient = false) {
                 const bool self = missing(u, u), one = missing(u, KEY_ONE), with_yc = missing(u, KEY_YC);
                 bool any = self || one || with_yc;
                 for (int32_t v : done)
@@ -918,7 +933,8 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
                     ch.ensure(u);
                     return;
                 }
-                ch.ensure_tos(u);
+                if (transient && !ch.resident(u)) ch.gen_term(u);
+                else ch.ensure_tos(u);
                 partners.clear();
                 pkeys.clear();
                 if (with_yc) { partners.push_back(yc_loc); pkeys.push_back(key(u, KEY_YC)); }
@@ -939,8 +955,15 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
             };
             if ((int32_t)N.size() <= room) {
                 std::vector<int32_t> done;
-                for (int32_t u : N) {
-                    reduce_term(u, done);
+                for (size_t q = 0; q < N.size(); ++q) {
+                    const int32_t u = N[q];
+                    bool transient = false;
+                    if (q + 1 == N.size() && lim.transient_horizon > 0) {
+                        const std::vector<int32_t> &occ = term_units[u];
+                        auto it = std::upper_bound(occ.begin(), occ.end(), ui);
+                        transient = it == occ.end() || *it > ui + lim.transient_horizon;
+                    }
+                    reduce_term(u, done, transient);
                     done.push_back(u);
                     if (!ch.err.empty()) return ch.err;
                 }

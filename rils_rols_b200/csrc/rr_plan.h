@@ -63,6 +63,7 @@ struct PlanLimits {
     int32_t target_chunks = 1;
     int32_t n_pins = RR_NPIN;     // pins the Gram plans may use (rr_isa.h); 0 = tile slots only
     int32_t n_cache = RR_NREG - RR_NPIN;  // cache registers for shared sub-expressions; 0 = off
+    int32_t transient_horizon = 4;  // a new term no candidate lists again within this many units is not stored
     bool no_cse = false;
 };
 
@@ -86,6 +87,7 @@ public:
     const std::vector<double> &cand_contract_w() const { return cand_w_; }
     // distinct terms (ascending ids) that contain shared sub-expression `sub`
     const std::vector<int32_t> &sub_occurrences(int32_t sub) const { return sub_occ_[sub]; }
+    int32_t sub_size(int32_t sub) const { return sub_size_[sub]; }  // nodes of the sub-expression
 
     // OLS_FIT, Gram path: Gram + A^T yc + column sums for the candidates in `subset`
     // (nullptr = all). cand_dot: per listed candidate m(m+1)/2 (upper triangle, row-major)
@@ -118,6 +120,7 @@ private:
     std::vector<int32_t> term_id_;
     std::vector<double> cand_w_;
     std::vector<std::vector<int32_t>> sub_occ_;
+    std::vector<int32_t> sub_size_;
     double w_contract_ = 0.0;
 
     std::string build_term(int32_t code_begin, int32_t code_len, Term &t) const;
