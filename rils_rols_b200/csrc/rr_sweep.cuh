@@ -263,11 +263,6 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         for (int s = 0; s < S; ++s) t[s] = 0.0;
         uint32_t cnt = 0, fl = 0;  // reductions emitted / flushed in this chunk and tile
         uint32_t ddcnt = 0;
-        double2 dd_next = make_double2(0.0, 0.0);  // running (hi, lo) of double-double output `ddcnt`, prefetched
-        if constexpr (SPECIAL) {
-            // double-double plans have even dot ids throughout (pairs); classifier-metric plans do not use this
-            if ((reinterpret_cast<uintptr_t>(rc.acc_row) & 15u) == 0) dd_next = __ldcg(reinterpret_cast<const double2 *>(rc.acc_row));
-        }
         // pins: registers of the PTX core (static indices only) or a local array of the generic path
         double pr[PAIRS ? RR_NREG * 4 : 1];
         double pl[RR_NREG][S];
@@ -525,41 +520,61 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                 }
                 case RI_MDOTDD:
                 case RI_DOTMDD: if constexpr (SPECIAL) {
-                    // a double-double plan holds double-double reductions only (rr_plan.cpp): they bypass the
-                    // ring; output i occupies the (hi, lo) pair at 2i in the warp's private row
+                    // A double-double plan holds double-double reductions only (rr_plan.cpp): they bypass the
+                    // ring; output i occupies the (hi, lo) pair at 2i in the warp's private row.
+                    // All (up to 10) outputs of the instruction are formed together: each is a serial chain
+                    // of ~100 dependent FP64 operations (error-free products, 5 double-double shuffle steps),
+                    // and the unrolled code lets the scheduler interleave the chains. Outputs that the
+                    // instruction does not ask for are computed on zeros and not stored.
                     const bool single = op == RI_DOTMDD;
                     const uint32_t mask = single ? 0u : (w0 >> 16) & 0xffu;
-                    const int has_self = single ? 0 : (w0 >> 8) & 1, has_one = single ? 0 : (w0 >> 9) & 1;
-#pragma unroll 1
-                    for (int o = -2; o <= RR_NPIN; ++o) {  // -2 self, -1 one, 0..7 pins, RR_NPIN: the tile column of DOTMDD
-                        if (o == -2 && !has_self) continue;
-                        if (o == -1 && !has_one) continue;
-                        if (o >= 0 && o < RR_NPIN && !((mask >> o) & 1u)) continue;
-                        if (o == RR_NPIN && !single) continue;
-                        double hi = 0.0, lo = 0.0;
+                    // wanted outputs in order: self, one, pins 0..7 (DOTMDD: the tile column takes slot 0)
+                    const uint32_t want = single ? 1u : (((w0 >> 8) & 3u) | (mask << 2));
+                    constexpr int NO = RR_NPIN + 2;
+                    double hi[NO], lo[NO];
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) {
+                        hi[o] = 0.0;
+                        lo[o] = 0.0;
+                        if (!((want >> o) & 1u)) continue;  // warp-uniform
 #pragma unroll
                         for (int s = 0; s < S; ++s) {
                             if (!valid[s]) continue;
-                            const double v = o == -2 ? t[s] : (o == -1 ? 1.0 : (o == RR_NPIN ? u[s] : pl[o & (RR_NPIN - 1)][s]));
-                            dd_add_prod(hi, lo, t[s], v);
+                            const double v = single ? u[s] : (o == 0 ? t[s] : (o == 1 ? 1.0 : pl[o >= 2 ? o - 2 : 0][s]));
+                            dd_add_prod(hi[o], lo[o], t[s], v);
                         }
+                    }
 #pragma unroll
-                        for (int m = 16; m > 0; m >>= 1) {
-                            const double h2 = __shfl_xor_sync(0xffffffffu, hi, m);
-                            const double l2_ = __shfl_xor_sync(0xffffffffu, lo, m);
-                            dd_add(hi, lo, h2, l2_);
+                    for (int m = 16; m > 0; m >>= 1) {
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) {
+                            const double h2 = __shfl_xor_sync(0xffffffffu, hi[o], m);
+                            const double l2_ = __shfl_xor_sync(0xffffffffu, lo[o], m);
+                            dd_add(hi[o], lo[o], h2, l2_);
                         }
-                        // one writer per (hi, lo) pair of the warp's row; the running pair was fetched while
-                        // the previous output was being reduced (an L2 round trip per output otherwise), and
-                        // the next one is requested now (rows are padded: reading one pair past the end is safe)
-                        {
-                            double *q = rc.acc_row + 2u * ddcnt;
-                            double ah = dd_next.x, al = dd_next.y;
-                            dd_next = __ldcg(reinterpret_cast<const double2 *>(q + 2));
-                            dd_add(ah, al, hi, lo);
-                            if (lane == 0) *reinterpret_cast<double2 *>(q) = make_double2(ah, al);
+                    }
+                    // one writer per (hi, lo) pair of the warp's row
+                    {
+                        double *q = rc.acc_row + 2u * ddcnt;
+                        const int n_out = __popc(want);
+                        double2 cur[NO];
+#pragma unroll
+                        for (int o = 0; o < NO; ++o)  // all running pairs first: one L2 round trip, not ten
+                            cur[o] = o < n_out ? __ldcg(reinterpret_cast<const double2 *>(q + 2 * o)) : make_double2(0.0, 0.0);
+                        int k = 0;
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) {
+                            if (!((want >> o) & 1u)) continue;
+                            // cur[] is indexed by the output's rank k among the wanted ones
+                            double ah = 0.0, al = 0.0;
+#pragma unroll
+                            for (int r = 0; r < NO; ++r)
+                                if (r == k) { ah = cur[r].x; al = cur[r].y; }
+                            dd_add(ah, al, hi[o], lo[o]);
+                            if (lane == 0) *reinterpret_cast<double2 *>(q + 2 * k) = make_double2(ah, al);
+                            ++k;
                         }
-                        ++ddcnt;
+                        ddcnt += (uint32_t)n_out;
                     }
                     if (!single && (w0 >> 24)) {  // fused "then pin t"
                         const int j = (int)(((w0 >> 24) - 1u) % RR_NREG);
