@@ -357,8 +357,9 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     const int64_t stride = round_up(std::max(P.n_dots, 1), 32) + 32;
     // keep the accumulator rows within a sane budget
     const size_t row_budget = (size_t)env_double("RR_B200_ACC_BYTES", 6e9);
-    while (gx > 1 && (size_t)gx * NW * stride * 8 > row_budget) gx = (gx + 1) / 2;
-    const int rows = gx * NW;  // one accumulator row per warp
+    const int rpb = dd ? NW : 1;  // accumulator rows per block: double-double plans keep one per warp
+    while (gx > 1 && (size_t)gx * rpb * stride * 8 > row_budget) gx = (gx + 1) / 2;
+    const int rows = gx * rpb;
 
     // the kernel streams whole windows of kInsWindow instructions: pad the tail with ENDs
     std::vector<RRIns> ins(P.ins);
@@ -385,6 +386,7 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     a.cols = e->d_cols.as<int32_t>();
     a.acc = e->d_acc.as<double>();
     a.acc_stride = stride;
+    a.acc_rows_per_block = rpb;
     a.stg = stg;
     a.ld_stg = ld_stg;
     a.n_tiles = n_tiles;

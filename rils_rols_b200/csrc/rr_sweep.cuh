@@ -35,12 +35,13 @@ namespace rr {
 constexpr int kInsWindow = RR_INS_WINDOW;  // instructions per shared-memory window (1 KB), two windows
 // Shared memory of a block besides its tile. Static: instruction windows + mbarriers, padded to 3072 bytes
 // so that the dynamic part starts 4096-aligned in the shared WINDOW (1 KB of it is reserved by the
-// system). Dynamic, in front of the tile: the reduction rings, 4 KB per warp, aligned to 4096 bytes of the
+// system). Dynamic, in front of the tile: the reduction rings, 4 KB per warp (plus 256 bytes of staging
+// row per warp behind them), aligned to 4096 bytes of the
 // window at run time (the PTX core wraps its ring pointer with one LOP3, which needs that alignment).
 // The host asks the kernel where its dynamic part starts (n_tiles < 0: probe) and adds the slack.
 constexpr size_t kSweepStaticBytes = 3072;
 constexpr size_t sweep_static_smem() { return kSweepStaticBytes; }
-constexpr size_t sweep_ring_smem(int warps, int slack) { return (size_t)warps * 4096 + (size_t)slack; }
+constexpr size_t sweep_ring_smem(int warps, int slack) { return (size_t)warps * (4096 + 256) + (size_t)slack; }
 
 struct SweepArgs {
     const double *X;        // engine matrix: columns (features, y, yc) of `ld` doubles
@@ -49,7 +50,8 @@ struct SweepArgs {
     const RRIns *ins;       // all chunks; every chunk is padded to a multiple of kInsWindow
     const RRChunk *chunks;
     const int32_t *cols;
-    double *acc;            // [gridDim.x * warps][acc_stride] per-warp accumulator rows
+    double *acc;            // [gridDim.x * acc_rows_per_block][acc_stride] accumulator rows
+    int32_t acc_rows_per_block;  // 1, or the number of warps for double-double plans
     int64_t acc_stride;
     double *stg;            // RI_STG target: column u at stg + u * ld_stg
     int64_t ld_stg;
@@ -142,14 +144,29 @@ __device__ __forceinline__ double rr_rare(uint32_t which, double x, double u)
     }
 }
 
-// The warp's reduction ring (see rr_sweep_core.cuh): 16 rows of 32 lanes. C++ twin of the PTX code,
+// The warp's reduction ring and the block's staging rows (see rr_sweep_core.cuh). C++ twin of the PTX code,
 // used by the generic interpreter and to drain what is pending at the end of a tile.
 struct RingCtx {
     uint32_t ring_w;         // warp ring base | lane * 8 (shared-space byte address, base 4096-aligned)
     uint32_t ra[4];          // this lane's 4 read addresses in ring half 0 when the warp transposes
-    double *acc_row;         // the warp's private accumulator row (+ chunk dot_base)
-    uint32_t lane;
+    uint32_t stage_sh;       // staging rows of the block: [warp][slot 0..3][8] doubles
+    uint32_t stage_w;        // stage_sh + warp * 256 + (lane & 7) * 8
+    double *acc_row;         // the block's accumulator row (+ chunk dot_base)
+    uint32_t lane, warp, n_warps;
 };
+// slots [0, n_slots) of every warp's staging row -> the block's accumulator row (reductions base + 8 slot + r)
+__device__ __forceinline__ void stage_combine(const RingCtx &rc, uint32_t cnt, uint32_t base, uint32_t n_slots)
+{
+    asm volatile("bar.sync 1;" ::: "memory");
+    if (rc.warp < n_slots && rc.lane < 8u) {
+        const uint32_t rd = rc.stage_sh + rc.warp * 64u + rc.lane * 8u;
+        double s = lds_f64(rd);
+        for (uint32_t w = 1; w < rc.n_warps; ++w) s += lds_f64(rd + w * 256u);
+        const uint32_t idx = base + rc.warp * 8u + rc.lane;
+        if (idx < cnt) atomicAdd(rc.acc_row + idx, s);  // RED.E.ADD.F64, one writer per address
+    }
+    asm volatile("bar.sync 1;" ::: "memory");
+}
 __device__ __forceinline__ void ring_flush(const RingCtx &rc, uint32_t cnt, uint32_t &fl)
 {
     __syncwarp();
@@ -161,10 +178,17 @@ __device__ __forceinline__ void ring_flush(const RingCtx &rc, uint32_t cnt, uint
     double s = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
     s += __shfl_xor_sync(0xffffffffu, s, 8);
     s += __shfl_xor_sync(0xffffffffu, s, 16);
-    const uint32_t idx = fl + (rc.lane & 7u);
-    if (rc.lane < 8u && idx < cnt) atomicAdd(rc.acc_row + idx, s);  // RED.E.ADD.F64, one writer per address
+    if (rc.lane < 8u) sts_f64(rc.stage_w + ((fl & 24u) << 3), s);
+    const bool full = (fl & 24u) == 24u;
     fl += 8;
     __syncwarp();
+    if (full) stage_combine(rc, cnt, fl - 32u, 4u);  // warp-uniform AND block-uniform: every warp runs the same stream
+}
+// end of a tile: flush what is pending in the ring, then combine the partly filled group of the staging rows
+__device__ __forceinline__ void ring_drain(const RingCtx &rc, uint32_t cnt, uint32_t &fl)
+{
+    while (fl < cnt) ring_flush(rc, cnt, fl);
+    if (fl & 31u) stage_combine(rc, cnt, fl & ~31u, (fl >> 3) & 3u);
 }
 __device__ __forceinline__ void ring_emit(const RingCtx &rc, uint32_t &cnt, uint32_t &fl, double v)
 {
@@ -209,10 +233,15 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     };
     const uint32_t dyn_sh = smem_u32(rr_dyn);
     const uint32_t ring_sh = (dyn_sh + 4095u) & ~4095u;  // rings of warps 0..NW-1, each 4096-aligned
-    double *const rr_tile = reinterpret_cast<double *>(rr_dyn + (ring_sh - dyn_sh) + NW * 4096u);
-    const uint32_t tile_sh = ring_sh + NW * 4096u + tbase;
+    const uint32_t stage_sh = ring_sh + NW * 4096u;          // staging rows: 256 bytes per warp
+    double *const rr_tile = reinterpret_cast<double *>(rr_dyn + (ring_sh - dyn_sh) + NW * (4096u + 256u));
+    const uint32_t tile_sh = stage_sh + NW * 256u + tbase;
     RingCtx rc;
     rc.lane = (uint32_t)lane;
+    rc.warp = (uint32_t)warp;
+    rc.n_warps = NW;
+    rc.stage_sh = stage_sh;
+    rc.stage_w = stage_sh + (uint32_t)warp * 256u + (uint32_t)(lane & 7) * 8u;
     rc.ring_w = ring_sh + (uint32_t)warp * 4096u + (uint32_t)lane * 8u;
     {
         const uint32_t r = lane & 7, q = lane >> 3;
@@ -220,7 +249,9 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         for (uint32_t i = 0; i < 4; ++i)
             rc.ra[i] = ring_sh + (uint32_t)warp * 4096u + r * 256u + (((4u * q + i + r) & 15u) << 4);
     }
-    rc.acc_row = a.acc + ((size_t)blockIdx.x * NW + warp) * (size_t)a.acc_stride + ch.dot_base;  // one row per warp
+    // one accumulator row per block; double-double plans (which bypass ring and staging) one per warp
+    rc.acc_row = a.acc + ((size_t)blockIdx.x * a.acc_rows_per_block + (a.acc_rows_per_block > 1 ? warp : 0)) * (size_t)a.acc_stride +
+                 ch.dot_base;
 
     if (tid == 0) {
         mbar_init(&mbar_tile, 1);
@@ -286,7 +317,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
             if (b == 0) { mbar_wait(&mbar_ins[0], ins_parity0); ins_parity0 ^= 1u; }
             else { mbar_wait(&mbar_ins[1], ins_parity1); ins_parity1 ^= 1u; }
             const uint4 *ib = ibuf[b];
-            if constexpr (!SPECIAL && PAIRS) {
+            if constexpr (!SPECIAL && PAIRS && NW == 4) {
                 if (!partial) {
                     // full tile: the PTX core runs the window; it hands back what it does not implement
                     uint32_t ibp = smem_u32(ib);
@@ -296,7 +327,10 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                         double imm;
                         const uint32_t code = rr_core_s4<COLB, HALFB>(t0, t1, t2, t3, pr, cnt, fl, ibp, w0, w1, imm, tile_sh,
                                                                       rc.ring_w, rc.acc_row, rc.lane, rc.ra[0], rc.ra[1],
-                                                                      rc.ra[2], rc.ra[3], xg, a.ld * 8);
+                                                                      rc.ra[2], rc.ra[3], xg, a.ld * 8, rc.stage_w,
+                                                                      stage_sh + (uint32_t)warp * 64u + (uint32_t)(lane & 7) * 8u,
+                                                                      (uint32_t)warp * 8u + (uint32_t)(lane & 7),
+                                                                      (warp < 4 && lane < 8) ? 1u : 0u);
                         if (code == 0) break;
                         if (code == 1) { running = false; break; }
                         switch (w0 & 0xffu) {
@@ -608,8 +642,8 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                 }
             }
         }
-        // drain the ring
-        while (fl < cnt) ring_flush(rc, cnt, fl);
+        // drain the ring and the staging rows
+        ring_drain(rc, cnt, fl);
         __syncthreads();  // every warp is done with the tile before it is overwritten
     }
 }
