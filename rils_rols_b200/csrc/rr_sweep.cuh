@@ -213,10 +213,11 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     constexpr uint32_t HALFB = T * 4u;  // byte offset of the second half of a column
     extern __shared__ __align__(128) unsigned char rr_dyn[];  // [slack][rings: NW x 16 rows x 32 lanes][tile: columns x T]
     __shared__ __align__(16) unsigned char rr_static[kSweepStaticBytes];
-    static_assert(2 * (kInsWindow + 1) * 16 + 3 * 8 <= kSweepStaticBytes, "static shared memory layout");
-    uint4(*ibuf)[kInsWindow + 1] = reinterpret_cast<uint4(*)[kInsWindow + 1]>(rr_static);
-    uint64_t &mbar_tile = *reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 1) * 16);
-    uint64_t *mbar_ins = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 1) * 16 + 8);
+    static_assert(2 * (kInsWindow + 2) * 16 + 3 * 8 <= kSweepStaticBytes, "static shared memory layout");
+    // each window is followed by its sentinel and one padding slot (the core prefetches one instruction ahead)
+    uint4(*ibuf)[kInsWindow + 2] = reinterpret_cast<uint4(*)[kInsWindow + 2]>(rr_static);
+    uint64_t &mbar_tile = *reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16);
+    uint64_t *mbar_ins = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16 + 8);
 
     if (a.n_tiles < 0) {
         if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.acc[0] = (double)smem_u32(rr_dyn);
@@ -261,6 +262,8 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         // the sentinel behind each window: never overwritten by the window copies
         ibuf[0][kInsWindow] = make_uint4(RI_WINEND, 0, 0, 0);
         ibuf[1][kInsWindow] = make_uint4(RI_WINEND, 0, 0, 0);
+        ibuf[0][kInsWindow + 1] = make_uint4(RI_END, 0, 0, 0);
+        ibuf[1][kInsWindow + 1] = make_uint4(RI_END, 0, 0, 0);
     }
     __syncthreads();
     uint32_t tile_parity = 0, ins_parity0 = 0, ins_parity1 = 0;
