@@ -70,6 +70,61 @@ uint32_t un_ins(uint32_t op)
     return RI_END;
 }
 
+// (term, term) -> reduction id: open addressing, linear probing; the planner does a few hundred lookups per
+// candidate, which made std::unordered_map the largest item of the plan time
+class DotMap {
+public:
+    explicit DotMap(size_t expect)
+    {
+        size_t cap = 64;
+        while (cap < expect * 2) cap <<= 1;
+        keys_.assign(cap, kEmpty);
+        vals_.assign(cap, 0);
+        mask_ = cap - 1;
+    }
+    const int32_t *find(uint64_t k) const
+    {
+        for (size_t i = hash(k) & mask_;; i = (i + 1) & mask_) {
+            if (keys_[i] == k) return &vals_[i];
+            if (keys_[i] == kEmpty) return nullptr;
+        }
+    }
+    void set(uint64_t k, int32_t v)
+    {
+        if ((n_ + 1) * 2 > keys_.size()) grow();
+        for (size_t i = hash(k) & mask_;; i = (i + 1) & mask_) {
+            if (keys_[i] == k) { vals_[i] = v; return; }
+            if (keys_[i] == kEmpty) { keys_[i] = k; vals_[i] = v; ++n_; return; }
+        }
+    }
+
+private:
+    static constexpr uint64_t kEmpty = 0x7fffffff7fffffffull;  // not a key: term ids are small, sentinels are -1, -2
+    static size_t hash(uint64_t k)
+    {
+        k ^= k >> 33;
+        k *= 0xff51afd7ed558ccdull;
+        k ^= k >> 33;
+        return (size_t)k;
+    }
+    void grow()
+    {
+        std::vector<uint64_t> ok;
+        std::vector<int32_t> ov;
+        ok.swap(keys_);
+        ov.swap(vals_);
+        keys_.assign(ok.size() * 2, kEmpty);
+        vals_.assign(ok.size() * 2, 0);
+        mask_ = keys_.size() - 1;
+        n_ = 0;
+        for (size_t i = 0; i < ok.size(); ++i)
+            if (ok[i] != kEmpty) set(ok[i], ov[i]);
+    }
+    std::vector<uint64_t> keys_;
+    std::vector<int32_t> vals_;
+    size_t mask_ = 0, n_ = 0;
+};
+
 // pre-patch value locations: a tile slot index, a staged column (STAGED | index) or a pin (PINREF | j)
 constexpr uint32_t STAGED = 0x8000u;
 constexpr uint32_t PINREF = 0x4000u;
@@ -888,7 +943,7 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
     cand_dot.clear();
     cand_dot_begin.assign(1, 0);
     // dot key -> id, global over the plan (a dot computed in an earlier chunk is simply reused)
-    std::unordered_map<uint64_t, int32_t> dots;
+    DotMap dots((size_t)units.size() * 8 + 64);
     const int64_t KEY_YC = -1, KEY_ONE = -2;
     auto key = [](int64_t a, int64_t b) -> uint64_t {
         if (a > b) std::swap(a, b);
@@ -903,7 +958,7 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
         for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
             const std::vector<int32_t> &T = units[ui].terms;
             const int32_t m = (int32_t)T.size();
-            auto missing = [&](int64_t a, int64_t b) { return dots.find(key(a, b)) == dots.end(); };
+            auto missing = [&](int64_t a, int64_t b) { return dots.find(key(a, b)) == nullptr; };
             // distinct terms that take part in a reduction that is still missing; a missing pair has
             // both ends in N (missing() is symmetric), so processing N in order emits each pair once,
             // when its later term is in t
@@ -949,9 +1004,9 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
                 ch.mdot(self, one, partners, dd, ids);
                 if (!ch.err.empty()) return;
                 size_t q = 0;
-                if (self) dots[key(u, u)] = ids[q++];
-                if (one) dots[key(u, KEY_ONE)] = ids[q++];
-                for (uint64_t k : pkeys) dots[k] = ids[q++];
+                if (self) dots.set(key(u, u), ids[q++]);
+                if (one) dots.set(key(u, KEY_ONE), ids[q++]);
+                for (uint64_t k : pkeys) dots.set(k, ids[q++]);
             };
             if ((int32_t)N.size() <= room) {
                 std::vector<int32_t> done;
@@ -988,12 +1043,20 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
             // index table of this candidate
             for (int32_t i = 0; i < m; ++i)
                 for (int32_t j = i; j < m; ++j) {
-                    auto it = dots.find(key(T[i], T[j]));
-                    if (it == dots.end()) return "internal: missing Gram dot";
-                    cand_dot.push_back(it->second);
+                    const int32_t *it = dots.find(key(T[i], T[j]));
+                    if (!it) return "internal: missing Gram dot";
+                    cand_dot.push_back(*it);
                 }
-            for (int32_t i = 0; i < m; ++i) cand_dot.push_back(dots[key(T[i], KEY_YC)]);
-            for (int32_t i = 0; i < m; ++i) cand_dot.push_back(dots[key(T[i], KEY_ONE)]);
+            for (int32_t i = 0; i < m; ++i) {
+                const int32_t *it = dots.find(key(T[i], KEY_YC));
+                if (!it) return "internal: missing Gram dot";
+                cand_dot.push_back(*it);
+            }
+            for (int32_t i = 0; i < m; ++i) {
+                const int32_t *it = dots.find(key(T[i], KEY_ONE));
+                if (!it) return "internal: missing Gram dot";
+                cand_dot.push_back(*it);
+            }
             cand_dot_begin.push_back((int32_t)cand_dot.size());
         }
         if (!ch.err.empty()) return ch.err;
