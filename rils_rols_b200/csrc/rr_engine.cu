@@ -3,7 +3,7 @@
 // Data layout in HBM (per engine = per GPU shard): one column-major matrix of d + 2 columns with
 // column stride ld = round_up(n, 1024) doubles, zero padded: features 0..d-1 (the vector<ArrayXd>
 // layout of /root/reference/rils_rols_cpp/rils_rols_cpp.cpp:675-698), y, and y - mean(y).
-// Everything else (instruction streams, per-warp accumulator rows, reduced dots, per-candidate
+// Everything else (instruction streams, per-block accumulator rows, reduced dots, per-candidate
 // solve workspaces, the materialised term matrix of the exact path) lives in grow-only device
 // buffers owned by the engine. There is no CPU fallback: without a CUDA device of compute
 // capability 10.x every entry point fails with RR_ERR_NO_DEVICE.
