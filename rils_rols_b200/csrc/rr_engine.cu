@@ -390,6 +390,7 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     a.stg = stg;
     a.ld_stg = ld_stg;
     a.n_tiles = n_tiles;
+    a.dd_ring = env_int("RR_B200_DD_RING", 1);
     CU(cudaEventRecord(e->ev[2], e->stream));
     kern<<<dim3(gx, n_chunks), cfg.TH, smem, e->stream>>>(a);
     CU(cudaGetLastError());
@@ -443,6 +444,7 @@ rr::PlanLimits limits_for(rr_engine *e, const SweepCfg &cfg, int n_cand)
     lim.tile_cols = cfg.tile_cols();
     if (e->slots_pref > 0) lim.max_slots = e->slots_pref;
     lim.no_cse = (e->flags & RR_FLAG_NO_CSE) != 0;
+    lim.fuse = env_int("RR_B200_FUSE", 1) != 0;
     const int T = cfg.T();
     const int n_tiles = (int)std::max<int64_t>(1, (e->n + T - 1) / T);
     // enough independent program chunks to occupy the GPU when there are few sample tiles

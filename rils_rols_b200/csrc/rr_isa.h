@@ -71,15 +71,31 @@ enum RRInsOp : uint32_t {
     RI_PIN0,
     RI_LDP0 = RI_PIN0 + RR_NREG,
     RI_USEP0 = RI_LDP0 + RR_NREG,
+    // ---- super-instructions (planner peephole, rr_plan.cpp close()): frequent sequences in one dispatch.
+    // Each is bit-identical to the sequence it replaces (same operations, same operand order).
+    RI_MULP0 = RI_USEP0 + RR_NREG,   // t = t * reg[j]        (USEP j; MUL_M)
+    RI_DIVP0 = RI_MULP0 + RR_NREG,   // t = t / reg[j]        (USEP j; DIV_M)
+    RI_RDIVP0 = RI_DIVP0 + RR_NREG,  // t = reg[j] / t        (USEP j; RDIV_M)
+    RI_CMULP0 = RI_RDIVP0 + RR_NREG, // t = imm * reg[j]      (LOAD_C; USEP j; MUL_M)
+    RI_CDIVP0 = RI_CMULP0 + RR_NREG, // t = imm / reg[j]      (LOAD_C; USEP j; DIV_M)
     // ---- forms with a tile-column operand tile[w1]: everything from RI_FIRST_M on ----
-    RI_FIRST_M = RI_USEP0 + RR_NREG,
+    RI_FIRST_M = RI_CDIVP0 + RR_NREG,
     RI_LOAD_M = RI_FIRST_M,  // t = tile[w1]
     RI_ADD_M, RI_SUB_M, RI_RSUB_M, RI_MUL_M, RI_DIV_M, RI_RDIV_M,  // t = t op tile[w1] / tile[w1] op t (R*)
     RI_AXPY,    // t = t + imm * tile[w1]  (product rounded, then sum: the c*term + ... chain of
                 //                          rils_rols_cpp.cpp:503-510)
     RI_DOTM,    // one reduction: t . tile[w1]
     RI_DOTMDD,  // the same in double-double (two ids)
-    RI_OPCOUNT
+    // super-instructions with a tile-column operand; a second column index rides in the low word of imm
+    RI_CMUL_M,    // t = imm * tile[w1]                          (LOAD_C; MUL_M)
+    RI_CDIV_M,    // t = imm / tile[w1]                          (LOAD_C; DIV_M)
+    RI_MUL_MM,    // t = tile[w1] * tile[lo32(imm)]              (LOAD_M; MUL_M)
+    RI_MUL_M_ST,  // t = t * tile[w1]; tile[lo32(imm)] = t       (MUL_M; ST)
+    RI_LDPMUL_M0,                             // t = reg[j] * tile[w1]   (LDP j; MUL_M)
+    RI_LDPDIV_M0 = RI_LDPMUL_M0 + RR_NREG,    // t = reg[j] / tile[w1]   (LDP j; DIV_M)
+    RI_LDMDIVP0 = RI_LDPDIV_M0 + RR_NREG,     // t = tile[w1] / reg[j]   (LOAD_M; USEP j; DIV_M)
+    RI_LAST_M = RI_LDMDIVP0 + RR_NREG - 1,
+    RI_OPCOUNT = RI_LAST_M + 1
 };
 
 enum RRRareOp : uint32_t { RR_POW = 0, RR_LT, RR_GT, RR_EQ, RR_NE, RR_MIN, RR_MAX };
@@ -90,6 +106,21 @@ enum : uint32_t {
     MD_ONE = 1u << 1,
     RR_MDOT_MAX_OUT = 8,  // outputs of one RI_MDOT (the kernel's reduction ring drains in groups of 8)
 };
+// "X; MDOT" in one dispatch: the instruction is X (aux otherwise unused) with RR_THEN_MDOT set and the
+// MDOT's aux bits OR-ed into w0; X's handler ends in the MDOT handler instead of a dispatch. Only for the
+// multiplication / division forms below (what a term's last operation is in a local-search neighbourhood).
+#define RR_THEN_MDOT 0x8000u
+#ifdef __CUDACC__
+#define RR_HD __host__ __device__
+#else
+#define RR_HD
+#endif
+RR_HD static inline bool rr_md_fusable(uint32_t op)
+{
+    return op == RI_MUL_M || op == RI_DIV_M || op == RI_RDIV_M || op == RI_DIV_C || op == RI_RDIV_C ||
+           (op >= RI_MULP0 && op < RI_FIRST_M) || op == RI_CMUL_M || op == RI_CDIV_M || op == RI_MUL_MM ||
+           (op >= RI_LDPMUL_M0 && op <= RI_LAST_M);
+}
 #define RR_W0(op, aux) ((uint32_t)(op) | ((uint32_t)(aux) << 8))
 #define RR_OP(w0) ((w0) & 0xffu)
 #define RR_AUX(w0) ((w0) >> 8)

@@ -65,6 +65,7 @@ struct PlanLimits {
     int32_t n_cache = RR_NREG - RR_NPIN;  // cache registers for shared sub-expressions; 0 = off
     int32_t transient_horizon = 4;  // a new term no candidate lists again within this many units is not stored
     bool no_cse = false;
+    bool fuse = true;  // super-instruction peephole (rr_isa.h)
 };
 
 // dot-id sentinels used in the per-candidate index tables

@@ -55,6 +55,7 @@ struct SweepArgs {
     int64_t acc_stride;
     double *stg;            // RI_STG target: column u at stg + u * ld_stg
     int64_t ld_stg;
+    int32_t dd_ring;        // double-double plans: 1 = warp reduction through the ring, 0 = shuffle tree
     int32_t n_tiles;        // < 0: probe, the kernel only reports the shared-window address of its dynamic part in acc[0]
 };
 
@@ -305,6 +306,38 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
             for (int i = 0; i < RR_NREG * 4; ++i) pr[i] = 0.0;
         }
         int use_pin = -1;  // generic path: pin redirected into the next tile-column operand
+        // RI_MDOT of the generic path (also the tail of an instruction carrying RR_THEN_MDOT)
+        auto mdot = [&](const uint32_t w0) {
+            if (w0 & (MD_SELF << 8)) {
+                double v = 0.0;
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (!partial || valid[s]) v = fma(t[s], t[s], v);
+                ring_emit(rc, cnt, fl, v);
+            }
+            if (w0 & (MD_ONE << 8)) {
+                double v = 0.0;
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (!partial || valid[s]) v += t[s];
+                ring_emit(rc, cnt, fl, v);
+            }
+            const uint32_t mask = (w0 >> 16) & 0xffu;
+#pragma unroll 1
+            for (int j = 0; j < RR_NPIN; ++j) {
+                if (!((mask >> j) & 1u)) continue;
+                double v = 0.0;
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (!partial || valid[s]) v = fma(t[s], pl[j][s], v);
+                ring_emit(rc, cnt, fl, v);
+            }
+            if (w0 >> 24) {  // fused "then pin t"
+                const int j = (int)(((w0 >> 24) - 1u) % RR_NREG);
+#pragma unroll
+                for (int s = 0; s < S; ++s) pl[j][s] = t[s];
+            }
+        };
 
         bool running = true;
         for (int win = 0; running; ++win) {
@@ -386,16 +419,50 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     use_pin = -1;
                 }
                 if (op >= RI_PIN0 && op < RI_FIRST_M) {
+                    // value-register forms, RR_NREG opcodes each: PIN, LDP, USEP and the fused MULP, DIVP, RDIVP, CMULP, CDIVP
                     const int j = (int)((op - RI_PIN0) % RR_NREG);
-                    if (op < RI_LDP0) {
+                    switch ((op - RI_PIN0) / RR_NREG) {
+                    case 0:
 #pragma unroll
                         for (int s = 0; s < S; ++s) pl[j][s] = t[s];
-                    } else if (op < RI_USEP0) {
+                        break;
+                    case 1:
 #pragma unroll
                         for (int s = 0; s < S; ++s) t[s] = pl[j][s];
-                    } else {
-                        use_pin = j;
+                        break;
+                    case 2: use_pin = j; break;
+                    case 3:
+#pragma unroll
+                        for (int s = 0; s < S; ++s) t[s] = __dmul_rn(t[s], pl[j][s]);
+                        break;
+                    case 4:
+#pragma unroll
+                        for (int s = 0; s < S; ++s) t[s] = __ddiv_rn(t[s], pl[j][s]);
+                        break;
+                    case 5:
+#pragma unroll
+                        for (int s = 0; s < S; ++s) t[s] = __ddiv_rn(pl[j][s], t[s]);
+                        break;
+                    case 6:
+#pragma unroll
+                        for (int s = 0; s < S; ++s) t[s] = __dmul_rn(imm, pl[j][s]);
+                        break;
+                    default:
+#pragma unroll
+                        for (int s = 0; s < S; ++s) t[s] = __ddiv_rn(imm, pl[j][s]);
+                        break;
                     }
+                    if ((w0 & RR_THEN_MDOT) && op >= RI_MULP0) mdot(w0);
+                    continue;
+                }
+                if (op >= RI_LDPMUL_M0) {
+                    // fused register / tile-column forms: LDPMUL_M, LDPDIV_M, LDMDIVP
+                    const int j = (int)((op - RI_LDPMUL_M0) % RR_NREG);
+                    const uint32_t kind = (op - RI_LDPMUL_M0) / RR_NREG;
+#pragma unroll
+                    for (int s = 0; s < S; ++s)
+                        t[s] = kind == 0 ? __dmul_rn(pl[j][s], u[s]) : (kind == 1 ? __ddiv_rn(pl[j][s], u[s]) : __ddiv_rn(u[s], pl[j][s]));
+                    if (w0 & RR_THEN_MDOT) mdot(w0);
                     continue;
                 }
                 switch (op) {
@@ -462,6 +529,29 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
 #pragma unroll
                     for (int s = 0; s < S; ++s) t[s] = __dmul_rn(t[s], u[s]);
                     break;
+                case RI_CMUL_M:
+#pragma unroll
+                    for (int s = 0; s < S; ++s) t[s] = __dmul_rn(imm, u[s]);
+                    break;
+                case RI_CDIV_M:
+#pragma unroll
+                    for (int s = 0; s < S; ++s) t[s] = __ddiv_rn(imm, u[s]);
+                    break;
+                case RI_MUL_MM: {
+                    const uint32_t col2 = tile_sh + in.z * COLB;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) t[s] = __dmul_rn(u[s], lds_f64(col2 + soff(s)));
+                    break;
+                }
+                case RI_MUL_M_ST: {
+                    const uint32_t col2 = tile_sh + in.z * COLB;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        t[s] = __dmul_rn(t[s], u[s]);
+                        sts_f64(col2 + soff(s), t[s]);
+                    }
+                    break;
+                }
                 case RI_DIV_C:
 #pragma unroll
                     for (int s = 0; s < S; ++s) t[s] = __ddiv_rn(t[s], imm);
@@ -523,38 +613,9 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     ring_emit(rc, cnt, fl, v);
                     break;
                 }
-                case RI_MDOT: {
-                    if (w0 & (MD_SELF << 8)) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int s = 0; s < S; ++s)
-                            if (!partial || valid[s]) v = fma(t[s], t[s], v);
-                        ring_emit(rc, cnt, fl, v);
-                    }
-                    if (w0 & (MD_ONE << 8)) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int s = 0; s < S; ++s)
-                            if (!partial || valid[s]) v += t[s];
-                        ring_emit(rc, cnt, fl, v);
-                    }
-                    const uint32_t mask = (w0 >> 16) & 0xffu;
-#pragma unroll 1
-                    for (int j = 0; j < RR_NPIN; ++j) {
-                        if (!((mask >> j) & 1u)) continue;
-                        double v = 0.0;
-#pragma unroll
-                        for (int s = 0; s < S; ++s)
-                            if (!partial || valid[s]) v = fma(t[s], pl[j][s], v);
-                        ring_emit(rc, cnt, fl, v);
-                    }
-                    if (w0 >> 24) {  // fused "then pin t"
-                        const int j = (int)(((w0 >> 24) - 1u) % RR_NREG);
-#pragma unroll
-                        for (int s = 0; s < S; ++s) pl[j][s] = t[s];
-                    }
+                case RI_MDOT:
+                    mdot(w0);
                     break;
-                }
                 case RI_MDOTDD:
                 case RI_DOTMDD: if constexpr (SPECIAL) {
                     // A double-double plan holds double-double reductions only (rr_plan.cpp): they bypass the
@@ -581,6 +642,52 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                             dd_add_prod(hi[o], lo[o], t[s], v);
                         }
                     }
+                    if (a.dd_ring) {
+                        // Warp reduction through the warp's ring (unused by double-double plans otherwise): the
+                        // k-th wanted output parks its 32 per-lane (hi, lo) pairs in row k (512 bytes); lane
+                        // (q, r) adds up a quarter of row r in double-double (rotated order: conflict-free), two
+                        // shuffle steps join the quarters, and lanes 0 .. n_out-1 each own one output's running
+                        // pair in the warp's private accumulator row. ~5x fewer operations than a 5-level
+                        // double-double shuffle tree per output, and the outputs' chains run in parallel lanes.
+                        const int n_out = __popc(want);  // <= RR_MDOT_MAX_OUT = 8 rows = the 4096-byte ring
+                        const uint32_t ring0 = rc.ring_w - rc.lane * 8u;
+                        __syncwarp();
+                        {
+                            uint32_t wr = ring0 + rc.lane * 16u;
+#pragma unroll
+                            for (int o = 0; o < NO; ++o) {
+                                if (!((want >> o) & 1u)) continue;
+                                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(wr), "d"(hi[o]), "d"(lo[o]) : "memory");
+                                wr += 512u;
+                            }
+                        }
+                        __syncwarp();
+                        const uint32_t r = rc.lane & 7u, q4 = rc.lane >> 3;
+                        double sh = 0.0, sl = 0.0;
+                        if ((int)r < n_out) {
+                            const uint32_t rd = ring0 + r * 512u + q4 * 128u;
+#pragma unroll
+                            for (uint32_t i = 0; i < 8; ++i) {
+                                double h2, l2_;
+                                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(h2), "=d"(l2_) : "r"(rd + (((i + r) & 7u) << 4)));
+                                dd_add(sh, sl, h2, l2_);
+                            }
+                        }
+#pragma unroll
+                        for (int m = 8; m <= 16; m <<= 1) {
+                            const double h2 = __shfl_xor_sync(0xffffffffu, sh, m);
+                            const double l2_ = __shfl_xor_sync(0xffffffffu, sl, m);
+                            dd_add(sh, sl, h2, l2_);
+                        }
+                        if ((int)rc.lane < n_out) {
+                            double2 *qp = reinterpret_cast<double2 *>(rc.acc_row + 2u * (ddcnt + rc.lane));
+                            double2 cur = __ldcg(qp);
+                            dd_add(cur.x, cur.y, sh, sl);
+                            *qp = cur;
+                        }
+                        ddcnt += (uint32_t)n_out;
+                        __syncwarp();
+                    } else {
 #pragma unroll
                     for (int m = 16; m > 0; m >>= 1) {
 #pragma unroll
@@ -613,6 +720,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                         }
                         ddcnt += (uint32_t)n_out;
                     }
+                    }
                     if (!single && (w0 >> 24)) {  // fused "then pin t"
                         const int j = (int)(((w0 >> 24) - 1u) % RR_NREG);
 #pragma unroll
@@ -643,6 +751,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                 default:
                     break;
                 }
+                if ((w0 & RR_THEN_MDOT) && rr_md_fusable(op)) mdot(w0);
             }
         }
         // drain the ring and the staging rows

@@ -22,12 +22,27 @@ RR_NREG = 10
 RR_INS_WINDOW = 64
 RI_LDP0 = RI_PIN0 + RR_NREG
 RI_USEP0 = RI_LDP0 + RR_NREG
-RI_FIRST_M = RI_USEP0 + RR_NREG
+RI_MULP0 = RI_USEP0 + RR_NREG
+RI_DIVP0 = RI_MULP0 + RR_NREG
+RI_RDIVP0 = RI_DIVP0 + RR_NREG
+RI_CMULP0 = RI_RDIVP0 + RR_NREG
+RI_CDIVP0 = RI_CMULP0 + RR_NREG
+RI_FIRST_M = RI_CDIVP0 + RR_NREG
 (RI_LOAD_M, RI_ADD_M, RI_SUB_M, RI_RSUB_M, RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_AXPY, RI_DOTM,
- RI_DOTMDD) = range(RI_FIRST_M, RI_FIRST_M + 10)
+ RI_DOTMDD, RI_CMUL_M, RI_CDIV_M, RI_MUL_MM, RI_MUL_M_ST, RI_LDPMUL_M0) = range(RI_FIRST_M, RI_FIRST_M + 15)
+RI_LDPDIV_M0 = RI_LDPMUL_M0 + RR_NREG
+RI_LDMDIVP0 = RI_LDPDIV_M0 + RR_NREG
+RI_OPCOUNT = RI_LDMDIVP0 + RR_NREG
 RR_MDOT_MAX_OUT = 8
 RR_POW, RR_LT, RR_GT, RR_EQ, RR_NE, RR_MIN, RR_MAX = range(7)
 RB_CONST, RB_SWAP = 1 << 4, 1 << 5
+RR_THEN_MDOT = 0x8000
+
+
+def md_fusable(op: int) -> bool:
+    return (op in (RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_DIV_C, RI_RDIV_C, RI_CMUL_M, RI_CDIV_M, RI_MUL_MM)
+            or RI_MULP0 <= op < RI_FIRST_M or RI_LDPMUL_M0 <= op < RI_OPCOUNT)
+
 
 INS_DT = np.dtype([("w0", "<u4"), ("w1", "<u4"), ("imm", "<f8")])
 CHUNK_DT = np.dtype([("pc_begin", "<i4"), ("n_ins", "<i4"), ("dot_base", "<i4"), ("n_dots", "<i4"),
@@ -89,6 +104,27 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
     n = cols_global.shape[1]
     dots = np.zeros(max(plan.n_dots, 1))
     stg = np.zeros((n_stg, n))
+
+    def do_mdot(op, aux, t, pins, out):
+        step = 2 if op == RI_MDOTDD else 1
+        vals = []
+        if aux & 1: vals.append(float(np.dot(t, t)))
+        if aux & 2: vals.append(float(np.sum(t)))
+        mask = (aux >> 8) & 0xFF
+        for j in range(RR_NPIN):
+            if mask >> j & 1:
+                assert pins[j] is not None, "MDOT against an empty pin"
+                vals.append(float(np.dot(t, pins[j])))
+        assert 0 < len(vals) <= RR_MDOT_MAX_OUT
+        for v in vals:
+            dots[out] += v
+            out += step
+        if aux >> 16:  # fused "then pin t"
+            j = (aux >> 16) - 1
+            assert j < RR_NREG and not (mask >> j & 1)
+            pins[j] = t.copy()
+        return out
+
     with np.errstate(all="ignore"):
         for ch in plan.chunks:
             ncols = int(ch["n_cols"])
@@ -101,6 +137,7 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
             end = pc + int(ch["n_ins"])
             while pc < end:
                 w0, w1, imm = int(plan.ins["w0"][pc]), int(plan.ins["w1"][pc]), float(plan.ins["imm"][pc])
+                col2 = int(plan.ins["imm"][pc:pc + 1].view(np.uint64)[0] & 0xFFFFFFFF)  # second column of the fused forms
                 pc += 1
                 op, aux = w0 & 0xFF, w0 >> 8
                 src = None
@@ -147,6 +184,29 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 elif RI_USEP0 <= op < RI_USEP0 + RR_NREG:
                     assert (pc - 1 - int(ch["pc_begin"])) % RR_INS_WINDOW != RR_INS_WINDOW - 1, "USEP at a window end"
                     use_pin = op - RI_USEP0
+                elif RI_MULP0 <= op < RI_FIRST_M:  # fused value-register forms
+                    j = (op - RI_MULP0) % RR_NREG
+                    assert pins[j] is not None, "fused form reads an empty value register"
+                    kind = (op - RI_MULP0) // RR_NREG
+                    if kind == 0: t = t * pins[j]
+                    elif kind == 1: t = t / pins[j]
+                    elif kind == 2: t = pins[j] / t
+                    elif kind == 3: t = imm * pins[j]
+                    else: t = imm / pins[j]
+                elif op == RI_CMUL_M: t = imm * src
+                elif op == RI_CDIV_M: t = imm / src
+                elif op == RI_MUL_MM:
+                    assert col2 < plan.max_tile_cols, f"tile column {col2} out of range"
+                    t = src * tile[col2]
+                elif op == RI_MUL_M_ST:
+                    assert col2 < plan.max_tile_cols, f"tile column {col2} out of range"
+                    t = t * src
+                    tile[col2] = t.copy()
+                elif RI_LDPMUL_M0 <= op < RI_OPCOUNT:
+                    j = (op - RI_LDPMUL_M0) % RR_NREG
+                    assert pins[j] is not None, "fused form reads an empty value register"
+                    kind = (op - RI_LDPMUL_M0) // RR_NREG
+                    t = pins[j] * src if kind == 0 else (pins[j] / src if kind == 1 else src / pins[j])
                 elif op == RI_SIN: t = np.sin(t)
                 elif op == RI_COS: t = np.cos(t)
                 elif op == RI_LN: t = np.log(t)
@@ -165,23 +225,7 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     elif r == RR_MIN: t = np.where(x < v, x, v)
                     else: t = np.where(x > v, x, v)
                 elif op in (RI_MDOT, RI_MDOTDD):
-                    step = 2 if op == RI_MDOTDD else 1
-                    vals = []
-                    if aux & 1: vals.append(float(np.dot(t, t)))
-                    if aux & 2: vals.append(float(np.sum(t)))
-                    mask = (aux >> 8) & 0xFF
-                    for j in range(RR_NPIN):
-                        if mask >> j & 1:
-                            assert pins[j] is not None, "MDOT against an empty pin"
-                            vals.append(float(np.dot(t, pins[j])))
-                    assert 0 < len(vals) <= RR_MDOT_MAX_OUT
-                    for v in vals:
-                        dots[out] += v
-                        out += step
-                    if aux >> 16:  # fused "then pin t"
-                        j = (aux >> 16) - 1
-                        assert j < RR_NREG and not (mask >> j & 1)
-                        pins[j] = t.copy()
+                    out = do_mdot(op, aux, t, pins, out)
                 elif op == RI_CLSMET:
                     y = tile[w1]
                     ypb, yb = (t >= 0.5).astype(float), (y >= 0.5).astype(float)
@@ -192,6 +236,8 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     out += 3
                 else:
                     raise AssertionError(f"bad opcode {op}")
+                if (w0 & RR_THEN_MDOT) and md_fusable(op):  # "X; MDOT" in one instruction
+                    out = do_mdot(RI_MDOT, aux & ~(RR_THEN_MDOT >> 8), t, pins, out)
             assert out == int(ch["dot_base"]) + int(ch["n_dots"]), "chunk dot count mismatch"
     return dots[: plan.n_dots], stg
 
