@@ -445,6 +445,7 @@ rr::PlanLimits limits_for(rr_engine *e, const SweepCfg &cfg, int n_cand)
     if (e->slots_pref > 0) lim.max_slots = e->slots_pref;
     lim.no_cse = (e->flags & RR_FLAG_NO_CSE) != 0;
     lim.fuse = env_int("RR_B200_FUSE", 1) != 0;
+    lim.mdot_rows = cfg.S == 4 && cfg.TH == 128;  // what rr_core_s4 expects behind every RI_MDOT carrier
     const int T = cfg.T();
     const int n_tiles = (int)std::max<int64_t>(1, (e->n + T - 1) / T);
     // enough independent program chunks to occupy the GPU when there are few sample tiles

@@ -109,6 +109,12 @@ enum : uint32_t {
 // "X; MDOT" in one dispatch: the instruction is X (aux otherwise unused) with RR_THEN_MDOT set and the
 // MDOT's aux bits OR-ed into w0; X's handler ends in the MDOT handler instead of a dispatch. Only for the
 // multiplication / division forms below (what a term's last operation is in a local-search neighbourhood).
+// Data slot behind an instruction that ends in an RI_MDOT (plans for the 4-samples-per-thread core):
+// opcode RI_NOP with aux = RR_MDOT_ROWS; bytes 4..13 of the slot (w1, then imm) hold the ring row (0..15)
+// of the 10 potential outputs self, one, pins 0..7. The core reads them from its prefetch registers and
+// skips the slot; every other interpreter executes the slot as the NOP it is and derives the rows from
+// its running count (the two agree by construction; tests/isa_emu.py checks it).
+#define RR_MDOT_ROWS 1u
 #define RR_THEN_MDOT 0x8000u
 #ifdef __CUDACC__
 #define RR_HD __host__ __device__

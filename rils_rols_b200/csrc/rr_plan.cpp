@@ -886,7 +886,53 @@ struct BatchPlanner::Chunk {
             P.ins.resize(pc_begin);
             P.ins.insert(P.ins.end(), out.begin(), out.end());
         }
-        // USEP and its consumer stay inside one instruction window (rr_isa.h RR_INS_WINDOW)
+        // Ring rows of the reductions, decided here instead of in the kernel (rr_isa.h RR_MDOT_ROWS): the
+        // stream is straight-line, so the number of reductions emitted before an instruction - and with it
+        // the ring row (count & 15) of each of its outputs - is known statically. Every instruction that
+        // ends in an RI_MDOT is followed by a data slot holding the row of each of the 10 potential outputs
+        // (self, one, pins 0..7); an output that is not wanted gets the row of the next wanted one (which
+        // overwrites it) or the first free row behind this instruction's outputs.
+        auto carries_mdot = [](const RRIns &x) {
+            const uint32_t op = RR_OP(x.w0);
+            return op == RI_MDOT || ((x.w0 & RR_THEN_MDOT) && rr_md_fusable(op));
+        };
+        if (lim.mdot_rows) {
+            std::vector<RRIns> out;
+            out.reserve(P.ins.size() - pc_begin + 1024);
+            uint32_t cnt = 0;
+            for (size_t i = pc_begin; i < P.ins.size(); ++i) {
+                const RRIns &x = P.ins[i];
+                const uint32_t op = RR_OP(x.w0);
+                out.push_back(x);
+                if (carries_mdot(x)) {
+                    const uint32_t want = ((x.w0 >> 8) & 3u) | (((x.w0 >> 16) & 0xffu) << 2);
+                    uint8_t rows[16] = {0};
+                    uint32_t r = cnt;
+                    for (int o = 0; o < 10; ++o)
+                        if ((want >> o) & 1u) rows[o] = (uint8_t)(r++ & 15u);
+                    uint8_t next = (uint8_t)(r & 15u);
+                    for (int o = 9; o >= 0; --o) {
+                        if ((want >> o) & 1u) next = rows[o];
+                        else rows[o] = next;
+                    }
+                    cnt = r;
+                    RRIns d;
+                    std::memset(&d, 0, sizeof(d));
+                    d.w0 = RR_W0(RI_NOP, RR_MDOT_ROWS);
+                    std::memcpy(&d.w1, rows, 4);
+                    std::memcpy(&d.imm, rows + 4, 8);
+                    out.push_back(d);
+                } else if (op == RI_DOTM) {
+                    cnt += 1;
+                } else if (op == RI_CLSMET) {
+                    cnt += 3;
+                }
+            }
+            P.ins.resize(pc_begin);
+            P.ins.insert(P.ins.end(), out.begin(), out.end());
+        }
+        // USEP and its consumer, and an RI_MDOT carrier and its data slot, stay inside one instruction
+        // window (rr_isa.h RR_INS_WINDOW)
         {
             std::vector<RRIns> out;
             out.reserve(P.ins.size() - pc_begin + 16);
@@ -895,7 +941,8 @@ struct BatchPlanner::Chunk {
             nop.w0 = RI_NOP;
             for (size_t i = pc_begin; i < P.ins.size(); ++i) {
                 const uint32_t op = RR_OP(P.ins[i].w0);
-                if (op >= RI_USEP0 && op < RI_USEP0 + RR_NREG && out.size() % RR_INS_WINDOW == RR_INS_WINDOW - 1)
+                const bool pair_head = (op >= RI_USEP0 && op < RI_USEP0 + RR_NREG) || (lim.mdot_rows && carries_mdot(P.ins[i]));
+                if (pair_head && out.size() % RR_INS_WINDOW == RR_INS_WINDOW - 1)
                     out.push_back(nop);
                 out.push_back(P.ins[i]);
             }
@@ -1382,6 +1429,7 @@ extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kin
         lim.target_chunks = std::max(1, target_chunks);
         lim.no_cse = no_cse != 0;
         lim.n_pins = n_pins;
+        lim.mdot_rows = std::getenv("RR_B200_DEBUG_NO_MDROWS") == nullptr;  // as for the 4-samples-per-thread core
         rr::ColIds cols{d, d + 1};
         switch (kind) {
         case 0: err = bp.plan_gram(lim, cols, nullptr, false, P, tab, tab_begin); break;

@@ -66,6 +66,7 @@ struct PlanLimits {
     int32_t transient_horizon = 4;  // a new term no candidate lists again within this many units is not stored
     bool no_cse = false;
     bool fuse = true;  // super-instruction peephole (rr_isa.h)
+    bool mdot_rows = false;  // data slot with the ring rows behind every instruction that ends in RI_MDOT (rr_isa.h)
 };
 
 // dot-id sentinels used in the per-candidate index tables

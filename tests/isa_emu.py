@@ -37,6 +37,24 @@ RR_MDOT_MAX_OUT = 8
 RR_POW, RR_LT, RR_GT, RR_EQ, RR_NE, RR_MIN, RR_MAX = range(7)
 RB_CONST, RB_SWAP = 1 << 4, 1 << 5
 RR_THEN_MDOT = 0x8000
+RR_MDOT_ROWS = 1
+
+
+def ring_rows(aux: int, cnt: int):
+    """Rows (count & 15) of the 10 potential outputs self, one, pins 0..7 of an RI_MDOT with this aux when
+    `cnt` reductions went through the ring before it; an unwanted output takes the row of the next wanted
+    one or the first free row (rr_plan.cpp close())."""
+    want = (aux & 3) | (((aux >> 8) & 0xFF) << 2)
+    rows, r = [0] * 10, cnt
+    for o in range(10):
+        if want >> o & 1:
+            rows[o] = r & 15
+            r += 1
+    nxt = r & 15
+    for o in range(9, -1, -1):
+        if want >> o & 1: nxt = rows[o]
+        else: rows[o] = nxt
+    return rows, r
 
 
 def md_fusable(op: int) -> bool:
@@ -96,6 +114,7 @@ class Plan:
         self.n_terms_distinct = out.n_terms_distinct
         self.w_issued, self.w_contract = out.w_issued, out.w_contract
         self.kind = kind
+        self.has_rows = bool(((self.ins["w0"] & 0xFFFF) == (RI_NOP | RR_MDOT_ROWS << 8)).any())
         L.rr_debug_plan_free(C.byref(out))
 
 
@@ -132,10 +151,14 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
             t = np.zeros(n)
             pins = [None] * RR_NREG
             use_pin = -1
+            ring_cnt = 0          # reductions pushed through the warp ring so far (kernel: cnt)
+            rows_expected = None  # set by an RI_MDOT carrier, checked against the data slot behind it
             out = int(ch["dot_base"])
             pc = int(ch["pc_begin"])
             end = pc + int(ch["n_ins"])
             while pc < end:
+                assert rows_expected is None or (int(plan.ins["w0"][pc]) & 0xFFFF) == (RI_NOP | RR_MDOT_ROWS << 8) \
+                    or not plan.has_rows, "RI_MDOT carrier without its data slot"
                 w0, w1, imm = int(plan.ins["w0"][pc]), int(plan.ins["w1"][pc]), float(plan.ins["imm"][pc])
                 col2 = int(plan.ins["imm"][pc:pc + 1].view(np.uint64)[0] & 0xFFFFFFFF)  # second column of the fused forms
                 pc += 1
@@ -153,7 +176,14 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 use_pin = -1
                 if op == RI_END:
                     break
-                elif op == RI_NOP: pass
+                elif op == RI_NOP:
+                    if aux == RR_MDOT_ROWS:  # data slot: the ring rows of the preceding instruction's reductions
+                        assert rows_expected is not None, "MDOT data slot without an MDOT in front"
+                        got = list(plan.ins[pc - 1:pc].view(np.uint8)[4:14])
+                        assert got == rows_expected, f"ring rows {got} != {rows_expected}"
+                        assert (pc - 1 - int(ch["pc_begin"])) % RR_INS_WINDOW != 0, "data slot at a window start"
+                        rows_expected = None
+                        continue
                 elif op == RI_LOAD_C: t = np.full(n, imm)
                 elif op == RI_LOAD_M: t = src.copy()
                 elif op == RI_ST:
@@ -177,6 +207,7 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 elif op in (RI_DOTM, RI_DOTMDD):
                     dots[out] += float(np.dot(t, src))
                     out += 2 if op == RI_DOTMDD else 1
+                    ring_cnt += 1 if op == RI_DOTM else 0
                 elif RI_PIN0 <= op < RI_PIN0 + RR_NREG: pins[op - RI_PIN0] = t.copy()
                 elif RI_LDP0 <= op < RI_LDP0 + RR_NREG:
                     assert pins[op - RI_LDP0] is not None, "LDP of an empty pin"
@@ -226,6 +257,8 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     else: t = np.where(x > v, x, v)
                 elif op in (RI_MDOT, RI_MDOTDD):
                     out = do_mdot(op, aux, t, pins, out)
+                    if op == RI_MDOT:
+                        rows_expected, ring_cnt = ring_rows(aux, ring_cnt)
                 elif op == RI_CLSMET:
                     y = tile[w1]
                     ypb, yb = (t >= 0.5).astype(float), (y >= 0.5).astype(float)
@@ -234,10 +267,12 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     dots[out + 1] += float(-np.sum((1.0 - yb) * np.log(1.0 - prob) + yb * np.log(prob)))
                     dots[out + 2] += float(np.sum(np.abs(yb - t)))
                     out += 3
+                    ring_cnt += 3
                 else:
                     raise AssertionError(f"bad opcode {op}")
                 if (w0 & RR_THEN_MDOT) and md_fusable(op):  # "X; MDOT" in one instruction
                     out = do_mdot(RI_MDOT, aux & ~(RR_THEN_MDOT >> 8), t, pins, out)
+                    rows_expected, ring_cnt = ring_rows(aux, ring_cnt)
             assert out == int(ch["dot_base"]) + int(ch["n_dots"]), "chunk dot count mismatch"
     return dots[: plan.n_dots], stg
 
