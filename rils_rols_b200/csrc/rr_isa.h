@@ -51,6 +51,11 @@ enum RRInsOp : uint32_t {
     RI_STG,     // out[w1][sample] = t   (materialise a column in global memory)
     RI_LDG,     // t = X[w1][sample]     (engine column straight from global memory, not staged)
     RI_NOP,     // padding (see RR_INS_WINDOW)
+    RI_COMBINE, // plans for the 4-samples-per-thread core: the block's warps add up the 32 reductions parked in their
+                // staging rows and RED them to the block's accumulator row. The planner places it behind the
+                // instruction whose flush filled the fourth staging slot (flushes happen at statically known
+                // points), which keeps the block barrier out of the reduction handlers. Every other interpreter
+                // combines inside its flush and executes this as a NOP.
     RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C, RI_RDIV_C,  // t = t op imm / imm op t (R*)
     RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR,  // t = f(t)
     // rarely generated operators share one case: aux = RRRareOp | RB_CONST | RB_SWAP

@@ -781,7 +781,7 @@ struct BatchPlanner::Chunk {
                 const RRIns &x = P.ins[i];
                 const uint32_t op = RR_OP(x.w0);
                 if (op >= RI_PIN0 && op < RI_PIN0 + RR_NPIN && i + 1 < P.ins.size() &&
-                    (RR_OP(P.ins[i + 1].w0) == RI_MDOT || RR_OP(P.ins[i + 1].w0) == RI_MDOTDD) &&
+                    ((RR_OP(P.ins[i + 1].w0) == RI_MDOT && !lim.mdot_rows) || RR_OP(P.ins[i + 1].w0) == RI_MDOTDD) &&
                     !(P.ins[i + 1].w0 >> 24) && !((P.ins[i + 1].w0 >> (16 + (op - RI_PIN0))) & 1u)) {
                     RRIns m = P.ins[i + 1];
                     m.w0 |= (op - RI_PIN0 + 1u) << 24;
@@ -899,12 +899,18 @@ struct BatchPlanner::Chunk {
         if (lim.mdot_rows) {
             std::vector<RRIns> out;
             out.reserve(P.ins.size() - pc_begin + 1024);
-            uint32_t cnt = 0;
+            uint32_t cnt = 0, fl = 0;  // reductions pushed / flushed, exactly as the kernel counts them
+            RRIns comb;
+            std::memset(&comb, 0, sizeof(comb));
+            comb.w0 = RI_COMBINE;
             for (size_t i = pc_begin; i < P.ins.size(); ++i) {
                 const RRIns &x = P.ins[i];
                 const uint32_t op = RR_OP(x.w0);
                 out.push_back(x);
+                bool flushed = false;
                 if (carries_mdot(x)) {
+                    // RI_MDOT flushes 8 rows on entry when 8 or more are pending, then pushes
+                    if (cnt - fl >= 8) { fl += 8; flushed = true; }
                     const uint32_t want = ((x.w0 >> 8) & 3u) | (((x.w0 >> 16) & 0xffu) << 2);
                     uint8_t rows[16] = {0};
                     uint32_t r = cnt;
@@ -923,10 +929,13 @@ struct BatchPlanner::Chunk {
                     std::memcpy(&d.imm, rows + 4, 8);
                     out.push_back(d);
                 } else if (op == RI_DOTM) {
+                    // RI_DOTM pushes, then flushes behind itself
                     cnt += 1;
+                    if (cnt - fl >= 8) { fl += 8; flushed = true; }
                 } else if (op == RI_CLSMET) {
-                    cnt += 3;
+                    cnt += 3;  // classifier plans never run in the core
                 }
+                if (flushed && (fl & 31u) == 0) out.push_back(comb);
             }
             P.ins.resize(pc_begin);
             P.ins.insert(P.ins.end(), out.begin(), out.end());

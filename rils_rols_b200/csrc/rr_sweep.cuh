@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     pc = kInsWindow;
                     break;
                 case RI_NOP:
+                case RI_COMBINE:  // this interpreter combines inside its flush (ring_flush)
                     break;
                 case RI_LOAD_C:
 #pragma unroll

@@ -17,8 +17,8 @@ from rils_rols_b200.batch import Batch, rr_batch
 
 RR_NPIN = 8
 RR_NREG = 10
-(RI_END, RI_WINEND, RI_LOAD_C, RI_ST, RI_STG, RI_LDG, RI_NOP, RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C,
- RI_RDIV_C, RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET, RI_PIN0) = range(24)
+(RI_END, RI_WINEND, RI_LOAD_C, RI_ST, RI_STG, RI_LDG, RI_NOP, RI_COMBINE, RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C,
+ RI_RDIV_C, RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET, RI_PIN0) = range(25)
 RR_INS_WINDOW = 64
 RI_LDP0 = RI_PIN0 + RR_NREG
 RI_USEP0 = RI_LDP0 + RR_NREG
@@ -152,6 +152,8 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
             pins = [None] * RR_NREG
             use_pin = -1
             ring_cnt = 0          # reductions pushed through the warp ring so far (kernel: cnt)
+            ring_fl = 0           # ... and flushed (kernel: fl); the core flushes 8 rows at a time
+            want_combine = False  # the last flush filled the fourth staging slot: RI_COMBINE must follow
             rows_expected = None  # set by an RI_MDOT carrier, checked against the data slot behind it
             out = int(ch["dot_base"])
             pc = int(ch["pc_begin"])
@@ -160,6 +162,8 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 assert rows_expected is None or (int(plan.ins["w0"][pc]) & 0xFFFF) == (RI_NOP | RR_MDOT_ROWS << 8) \
                     or not plan.has_rows, "RI_MDOT carrier without its data slot"
                 w0, w1, imm = int(plan.ins["w0"][pc]), int(plan.ins["w1"][pc]), float(plan.ins["imm"][pc])
+                if want_combine and plan.has_rows and (w0 & 0xFFFF) != (RI_NOP | RR_MDOT_ROWS << 8):
+                    assert (w0 & 0xFF) == RI_COMBINE, "missing RI_COMBINE behind the flush that filled the staging rows"
                 col2 = int(plan.ins["imm"][pc:pc + 1].view(np.uint64)[0] & 0xFFFFFFFF)  # second column of the fused forms
                 pc += 1
                 op, aux = w0 & 0xFF, w0 >> 8
@@ -176,6 +180,9 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 use_pin = -1
                 if op == RI_END:
                     break
+                elif op == RI_COMBINE:
+                    assert want_combine, "RI_COMBINE without a full group of staged reductions"
+                    want_combine = False
                 elif op == RI_NOP:
                     if aux == RR_MDOT_ROWS:  # data slot: the ring rows of the preceding instruction's reductions
                         assert rows_expected is not None, "MDOT data slot without an MDOT in front"
@@ -207,7 +214,11 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 elif op in (RI_DOTM, RI_DOTMDD):
                     dots[out] += float(np.dot(t, src))
                     out += 2 if op == RI_DOTMDD else 1
-                    ring_cnt += 1 if op == RI_DOTM else 0
+                    if op == RI_DOTM:  # pushes, then flushes behind itself
+                        ring_cnt += 1
+                        if ring_cnt - ring_fl >= 8:
+                            ring_fl += 8
+                            want_combine = ring_fl % 32 == 0
                 elif RI_PIN0 <= op < RI_PIN0 + RR_NREG: pins[op - RI_PIN0] = t.copy()
                 elif RI_LDP0 <= op < RI_LDP0 + RR_NREG:
                     assert pins[op - RI_LDP0] is not None, "LDP of an empty pin"
@@ -258,6 +269,9 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 elif op in (RI_MDOT, RI_MDOTDD):
                     out = do_mdot(op, aux, t, pins, out)
                     if op == RI_MDOT:
+                        if ring_cnt - ring_fl >= 8:  # flushes on entry, then pushes
+                            ring_fl += 8
+                            want_combine = ring_fl % 32 == 0
                         rows_expected, ring_cnt = ring_rows(aux, ring_cnt)
                 elif op == RI_CLSMET:
                     y = tile[w1]
@@ -272,6 +286,9 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     raise AssertionError(f"bad opcode {op}")
                 if (w0 & RR_THEN_MDOT) and md_fusable(op):  # "X; MDOT" in one instruction
                     out = do_mdot(RI_MDOT, aux & ~(RR_THEN_MDOT >> 8), t, pins, out)
+                    if ring_cnt - ring_fl >= 8:
+                        ring_fl += 8
+                        want_combine = ring_fl % 32 == 0
                     rows_expected, ring_cnt = ring_rows(aux, ring_cnt)
             assert out == int(ch["dot_base"]) + int(ch["n_dots"]), "chunk dot count mismatch"
     return dots[: plan.n_dots], stg
