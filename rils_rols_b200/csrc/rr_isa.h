@@ -41,7 +41,7 @@ static_assert(sizeof(RRIns) == 16, "RRIns must be 16 bytes");
 // The kernel streams a chunk's instructions through shared memory in windows of RR_INS_WINDOW, counted
 // from the chunk's first instruction. USEP and its consumer must sit in the same window (the redirected
 // operand lives in registers that do not survive a window switch): the planner pads with RI_NOP.
-#define RR_INS_WINDOW 60
+#define RR_INS_WINDOW 64
 
 enum RRInsOp : uint32_t {
     RI_END = 0,

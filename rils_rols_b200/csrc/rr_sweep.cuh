@@ -152,11 +152,6 @@ struct RingCtx {
     uint32_t ra[4];          // this lane's 4 read addresses in ring half 0 when the warp transposes
     uint32_t stage_sh;       // staging rows of the block: [warp][slot 0..3][8] doubles
     uint32_t stage_w;        // stage_sh + warp * 256 + (lane & 7) * 8
-    // Second copy of the staging rows (static shared memory; same as the first when the block is not 4 warps):
-    // groups of 32 reductions alternate between the two, so that the core's RI_COMBINE needs ONE block barrier:
-    // a copy is only written again two groups later, i.e. behind the next group's barrier, which every warp
-    // reaches after it has read this one. stage_alt = address of the second copy - address of the first.
-    uint32_t stage_alt;
     double *acc_row;         // the block's accumulator row (+ chunk dot_base)
     uint32_t lane, warp, n_warps;
 };
@@ -165,7 +160,7 @@ __device__ __forceinline__ void stage_combine(const RingCtx &rc, uint32_t cnt, u
 {
     asm volatile("bar.sync 1;" ::: "memory");
     if (rc.warp < n_slots && rc.lane < 8u) {
-        const uint32_t rd = rc.stage_sh + (((base >> 5) & 1u) ? rc.stage_alt : 0u) + rc.warp * 64u + rc.lane * 8u;
+        const uint32_t rd = rc.stage_sh + rc.warp * 64u + rc.lane * 8u;
         double s = lds_f64(rd);
         for (uint32_t w = 1; w < rc.n_warps; ++w) s += lds_f64(rd + w * 256u);
         const uint32_t idx = base + rc.warp * 8u + rc.lane;
@@ -184,7 +179,7 @@ __device__ __forceinline__ void ring_flush(const RingCtx &rc, uint32_t cnt, uint
     double s = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
     s += __shfl_xor_sync(0xffffffffu, s, 8);
     s += __shfl_xor_sync(0xffffffffu, s, 16);
-    if (rc.lane < 8u) sts_f64(rc.stage_w + (((fl >> 5) & 1u) ? rc.stage_alt : 0u) + ((fl & 24u) << 3), s);
+    if (rc.lane < 8u) sts_f64(rc.stage_w + ((fl & 24u) << 3), s);
     const bool full = (fl & 24u) == 24u;
     fl += 8;
     __syncwarp();
@@ -219,11 +214,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     constexpr uint32_t HALFB = T * 4u;  // byte offset of the second half of a column
     extern __shared__ __align__(128) unsigned char rr_dyn[];  // [slack][rings: NW x 16 rows x 32 lanes][tile: columns x T]
     __shared__ __align__(16) unsigned char rr_static[kSweepStaticBytes];
-    // [2 instruction windows, each + sentinel + padding slot][3 mbarriers][second copy of the staging rows, 4 warps]
-    constexpr uint32_t kStageAltOff = 2016;
-    static_assert(2 * (kInsWindow + 2) * 16 + 3 * 8 <= kStageAltOff && kStageAltOff % 16 == 0 &&
-                      kStageAltOff + 4 * 256 <= kSweepStaticBytes,
-                  "static shared memory layout");
+    static_assert(2 * (kInsWindow + 2) * 16 + 3 * 8 <= kSweepStaticBytes, "static shared memory layout");
     // each window is followed by its sentinel and one padding slot (the core prefetches one instruction ahead)
     uint4(*ibuf)[kInsWindow + 2] = reinterpret_cast<uint4(*)[kInsWindow + 2]>(rr_static);
     uint64_t &mbar_tile = *reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16);
@@ -252,7 +243,6 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     rc.warp = (uint32_t)warp;
     rc.n_warps = NW;
     rc.stage_sh = stage_sh;
-    rc.stage_alt = NW == 4 ? smem_u32(rr_static + kStageAltOff) - stage_sh : 0u;
     rc.stage_w = stage_sh + (uint32_t)warp * 256u + (uint32_t)(lane & 7) * 8u;
     rc.ring_w = ring_sh + (uint32_t)warp * 4096u + (uint32_t)lane * 8u;
     {
@@ -376,7 +366,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                                                                       rc.ra[2], rc.ra[3], xg, a.ld * 8, rc.stage_w,
                                                                       stage_sh + (uint32_t)warp * 64u + (uint32_t)(lane & 7) * 8u,
                                                                       (uint32_t)warp * 8u + (uint32_t)(lane & 7),
-                                                                      (warp < 4 && lane < 8) ? 1u : 0u, rc.stage_alt);
+                                                                      (warp < 4 && lane < 8) ? 1u : 0u);
                         if (code == 0) break;
                         if (code == 1) { running = false; break; }
                         switch (w0 & 0xffu) {

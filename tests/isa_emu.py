@@ -19,7 +19,7 @@ RR_NPIN = 8
 RR_NREG = 10
 (RI_END, RI_WINEND, RI_LOAD_C, RI_ST, RI_STG, RI_LDG, RI_NOP, RI_COMBINE, RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C,
  RI_RDIV_C, RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET, RI_PIN0) = range(25)
-RR_INS_WINDOW = 60
+RR_INS_WINDOW = 64
 RI_LDP0 = RI_PIN0 + RR_NREG
 RI_USEP0 = RI_LDP0 + RR_NREG
 RI_MULP0 = RI_USEP0 + RR_NREG
