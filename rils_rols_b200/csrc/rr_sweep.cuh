@@ -635,12 +635,23 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     for (int o = 0; o < NO; ++o) {
                         hi[o] = 0.0;
                         lo[o] = 0.0;
-                        if (!((want >> o) & 1u)) continue;  // warp-uniform
+                    }
+                    if (single) {
+#pragma unroll
+                        for (int s = 0; s < S; ++s)
+                            if (valid[s]) dd_add_prod(hi[0], lo[0], t[s], u[s]);
+                    } else {
+                        // all 10 potential outputs, wanted or not: ten independent chains per sample that the
+                        // scheduler interleaves (a branch per output would serialise them); what is not wanted
+                        // is not stored
 #pragma unroll
                         for (int s = 0; s < S; ++s) {
                             if (!valid[s]) continue;
-                            const double v = single ? u[s] : (o == 0 ? t[s] : (o == 1 ? 1.0 : pl[o >= 2 ? o - 2 : 0][s]));
-                            dd_add_prod(hi[o], lo[o], t[s], v);
+#pragma unroll
+                            for (int o = 0; o < NO; ++o) {
+                                const double v = o == 0 ? t[s] : (o == 1 ? 1.0 : pl[o >= 2 ? o - 2 : 0][s]);
+                                dd_add_prod(hi[o], lo[o], t[s], v);
+                            }
                         }
                     }
                     if (a.dd_ring) {
@@ -667,12 +678,17 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                         double sh = 0.0, sl = 0.0;
                         if ((int)r < n_out) {
                             const uint32_t rd = ring0 + r * 512u + q4 * 128u;
+                            double ph[8], pl8[8];
 #pragma unroll
-                            for (uint32_t i = 0; i < 8; ++i) {
-                                double h2, l2_;
-                                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(h2), "=d"(l2_) : "r"(rd + (((i + r) & 7u) << 4)));
-                                dd_add(sh, sl, h2, l2_);
-                            }
+                            for (uint32_t i = 0; i < 8; ++i)
+                                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ph[i]), "=d"(pl8[i]) : "r"(rd + (((i + r) & 7u) << 4)));
+                            // pairwise tree: 3 dependent double-double additions instead of 8
+#pragma unroll
+                            for (int w = 1; w < 8; w <<= 1)
+#pragma unroll
+                                for (int i = 0; i < 8; i += 2 * w) dd_add(ph[i], pl8[i], ph[i + w], pl8[i + w]);
+                            sh = ph[0];
+                            sl = pl8[0];
                         }
 #pragma unroll
                         for (int m = 8; m <= 16; m <<= 1) {
