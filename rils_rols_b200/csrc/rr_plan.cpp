@@ -125,6 +125,102 @@ private:
     size_t mask_ = 0, n_ = 0;
 };
 
+// Postfix code ranges of a batch as hash-table keys (terms and sub-expressions that are equal as programs:
+// same operators, same variable indices, bit-identical constants). Open addressing on a 64-bit hash of the
+// range; a hit is verified word by word against the stored representative, so equal hashes never merge
+// different programs.
+class CodeTable {
+public:
+    CodeTable(const rr_batch *b, size_t expect) : b_(b)
+    {
+        size_t cap = 64;
+        while (cap < expect * 2) cap <<= 1;
+        slot_.assign(cap, Slot{0, -1, 0, 0});
+        mask_ = cap - 1;
+    }
+    uint64_t hash_range(int32_t c0, int32_t c1) const
+    {
+        uint64_t h = 0x9e3779b97f4a7c15ull ^ (uint64_t)(c1 - c0);
+        for (int32_t i = c0; i < c1; ++i) {
+            const uint32_t w = b_->code[i];
+            const uint32_t op = RR_INS_OP(w);
+            uint64_t v = op;
+            if (op == RR_OP_CONST) {
+                uint64_t bits;
+                std::memcpy(&bits, &b_->consts[RR_INS_ARG(w)], 8);
+                v ^= bits * 0xff51afd7ed558ccdull;
+            } else if (op == RR_OP_VAR) {
+                v ^= (uint64_t)RR_INS_ARG(w) << 8;
+            }
+            h = (h ^ v) * 0xc4ceb9fe1a85ec53ull;
+            h ^= h >> 29;
+        }
+        return h;
+    }
+    // id of the stored range equal to [c0, c1), or -1
+    int32_t find(int32_t c0, int32_t c1) const
+    {
+        const uint64_t h = hash_range(c0, c1);
+        for (size_t i = (size_t)h & mask_;; i = (i + 1) & mask_) {
+            const Slot &e = slot_[i];
+            if (e.id < 0) return -1;
+            if (e.h == h && equal(e.c0, e.c1, c0, c1)) return e.id;
+        }
+    }
+    // id of the stored range equal to [c0, c1); stores it under new_id when there is none (returns new_id)
+    int32_t find_or_insert(int32_t c0, int32_t c1, int32_t new_id)
+    {
+        if ((n_ + 1) * 2 > slot_.size()) grow();
+        const uint64_t h = hash_range(c0, c1);
+        for (size_t i = (size_t)h & mask_;; i = (i + 1) & mask_) {
+            Slot &e = slot_[i];
+            if (e.id < 0) {
+                e = Slot{h, new_id, c0, c1};
+                ++n_;
+                return new_id;
+            }
+            if (e.h == h && equal(e.c0, e.c1, c0, c1)) return e.id;
+        }
+    }
+
+private:
+    struct Slot {
+        uint64_t h;
+        int32_t id, c0, c1;
+    };
+    bool equal(int32_t a0, int32_t a1, int32_t b0, int32_t b1) const
+    {
+        if (a1 - a0 != b1 - b0) return false;
+        for (int32_t i = 0; i < a1 - a0; ++i) {
+            const uint32_t wa = b_->code[a0 + i], wb = b_->code[b0 + i];
+            const uint32_t op = RR_INS_OP(wa);
+            if (op != RR_INS_OP(wb)) return false;
+            if (op == RR_OP_CONST) {
+                if (std::memcmp(&b_->consts[RR_INS_ARG(wa)], &b_->consts[RR_INS_ARG(wb)], 8) != 0) return false;
+            } else if (op == RR_OP_VAR) {
+                if (RR_INS_ARG(wa) != RR_INS_ARG(wb)) return false;
+            }
+        }
+        return true;
+    }
+    void grow()
+    {
+        std::vector<Slot> old;
+        old.swap(slot_);
+        slot_.assign(old.size() * 2, Slot{0, -1, 0, 0});
+        mask_ = slot_.size() - 1;
+        for (const Slot &e : old)
+            if (e.id >= 0) {
+                size_t i = (size_t)e.h & mask_;
+                while (slot_[i].id >= 0) i = (i + 1) & mask_;
+                slot_[i] = e;
+            }
+    }
+    const rr_batch *b_;
+    std::vector<Slot> slot_;
+    size_t mask_ = 0, n_ = 0;
+};
+
 // pre-patch value locations: a tile slot index, a staged column (STAGED | index) or a pin (PINREF | j)
 constexpr uint32_t STAGED = 0x8000u;
 constexpr uint32_t PINREF = 0x4000u;
@@ -191,38 +287,24 @@ std::string BatchPlanner::analyse(bool no_cse)
     if (b_->cand_term_begin[0] != 0 || b_->term_code_begin[0] != 0) return "offset arrays must start at 0";
     term_id_.assign(n_terms, -1);
     terms_.clear();
-    std::unordered_map<std::string, int32_t> seen;
-    std::string key;
+    CodeTable seen(b_, (size_t)n_terms / 4 + 64);
     for (int32_t t = 0; t < n_terms; ++t) {
         const int32_t c0 = b_->term_code_begin[t], c1 = b_->term_code_begin[t + 1];
         if (c1 <= c0) return "empty term program";
-        key.clear();
         for (int32_t i = c0; i < c1; ++i) {
             const uint32_t w = b_->code[i];
-            const uint32_t op = RR_INS_OP(w);
-            key.push_back((char)op);
-            if (op == RR_OP_CONST) {
-                const uint32_t a = RR_INS_ARG(w);
-                if ((int32_t)a >= b_->n_consts) return "constant index out of range";
-                char buf[8];
-                std::memcpy(buf, &b_->consts[a], 8);
-                key.append(buf, 8);
-            } else if (op == RR_OP_VAR) {
-                const uint32_t a = RR_INS_ARG(w);
-                key.append((const char *)&a, 4);
-            }
+            if (RR_INS_OP(w) == RR_OP_CONST && (int32_t)RR_INS_ARG(w) >= b_->n_consts) return "constant index out of range";
         }
+        const int32_t id = (int32_t)terms_.size();
         if (!no_cse) {
-            auto it = seen.find(key);
-            if (it != seen.end()) { term_id_[t] = it->second; continue; }
+            const int32_t hit = seen.find_or_insert(c0, c1, id);
+            if (hit != id) { term_id_[t] = hit; continue; }
         }
         Term tm;
         std::string err = build_term(c0, c1 - c0, tm);
         if (!err.empty()) return err;
-        const int32_t id = (int32_t)terms_.size();
         terms_.push_back(std::move(tm));
         term_id_[t] = id;
-        if (!no_cse) seen.emplace(key, id);
     }
     // subtree-level sharing: an inner subtree that is itself one of the batch's distinct terms can be
     // read from that term's slot when it is resident (neighbours are built by wrapping or combining
@@ -233,22 +315,8 @@ std::string BatchPlanner::analyse(bool no_cse)
             for (int32_t x = 0; x < root; ++x) {
                 TermNode &nd = tm.nodes[x];
                 if (nd.leaf()) continue;
-                key.clear();
-                for (int32_t i = tm.code_begin + nd.first; i <= tm.code_begin + x; ++i) {
-                    const uint32_t w = b_->code[i];
-                    const uint32_t op = RR_INS_OP(w);
-                    key.push_back((char)op);
-                    if (op == RR_OP_CONST) {
-                        char buf[8];
-                        std::memcpy(buf, &b_->consts[RR_INS_ARG(w)], 8);
-                        key.append(buf, 8);
-                    } else if (op == RR_OP_VAR) {
-                        const uint32_t a = RR_INS_ARG(w);
-                        key.append((const char *)&a, 4);
-                    }
-                }
-                auto it = seen.find(key);
-                if (it != seen.end()) nd.sub_term = it->second;
+                const int32_t hit = seen.find(tm.code_begin + nd.first, tm.code_begin + x + 1);
+                if (hit >= 0) nd.sub_term = hit;
             }
         }
     }
@@ -260,7 +328,7 @@ std::string BatchPlanner::analyse(bool no_cse)
     sub_size_.clear();
     if (!no_cse) {
         const double kMinW = 8.0;  // at least a division, a square root or a transcendental inside
-        std::unordered_map<std::string, int32_t> sub_seen;
+        CodeTable sub_seen(b_, terms_.size() * 2 + 64);
         std::vector<std::vector<int32_t>> occ;
         std::vector<int32_t> osize;
         std::vector<double> wsub;
@@ -273,29 +341,10 @@ std::string BatchPlanner::analyse(bool no_cse)
                 if (nd.leaf()) continue;
                 wsub[x] = kW[nd.op] + wsub[nd.left] + (nd.right >= 0 ? wsub[nd.right] : 0.0);
                 if (x == root || wsub[x] < kMinW) continue;
-                key.clear();
-                for (int32_t i = tm.code_begin + nd.first; i <= tm.code_begin + x; ++i) {
-                    const uint32_t w = b_->code[i];
-                    const uint32_t op = RR_INS_OP(w);
-                    key.push_back((char)op);
-                    if (op == RR_OP_CONST) {
-                        char buf[8];
-                        std::memcpy(buf, &b_->consts[RR_INS_ARG(w)], 8);
-                        key.append(buf, 8);
-                    } else if (op == RR_OP_VAR) {
-                        const uint32_t a = RR_INS_ARG(w);
-                        key.append((const char *)&a, 4);
-                    }
-                }
-                auto it = sub_seen.find(key);
-                int32_t id;
-                if (it == sub_seen.end()) {
-                    id = (int32_t)occ.size();
-                    sub_seen.emplace(key, id);
+                const int32_t id = sub_seen.find_or_insert(tm.code_begin + nd.first, tm.code_begin + x + 1, (int32_t)occ.size());
+                if (id == (int32_t)occ.size()) {
                     occ.emplace_back();
                     osize.push_back(x - nd.first + 1);
-                } else {
-                    id = it->second;
                 }
                 nd.sub_id = id;
                 if (occ[id].empty() || occ[id].back() != (int32_t)u) occ[id].push_back((int32_t)u);
