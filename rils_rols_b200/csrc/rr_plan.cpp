@@ -1488,6 +1488,7 @@ extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kin
         lim.no_cse = no_cse != 0;
         lim.n_pins = n_pins;
         lim.mdot_rows = std::getenv("RR_B200_DEBUG_NO_MDROWS") == nullptr;  // as for the 4-samples-per-thread core
+        lim.fuse = std::getenv("RR_B200_DEBUG_NO_FUSE") == nullptr;
         rr::ColIds cols{d, d + 1};
         switch (kind) {
         case 0: err = bp.plan_gram(lim, cols, nullptr, false, P, tab, tab_begin); break;

@@ -99,6 +99,50 @@ def test_gram_plan_reproduces_design_matrix_products(golden, cfg, prefix, no_cse
             assert plan.n_terms_distinct < 0.5 * batch.n_terms and plan.w_issued < plan.w_contract
 
 
+def _opcodes(plan):
+    return plan.ins["w0"] & 0xFF
+
+
+@pytest.mark.parametrize("kind", [EMU.KIND_GRAM, EMU.KIND_EVAL])
+@pytest.mark.parametrize("cfg,prefix", [("cfg1_toy", "ls3_"), ("cfg3_breast_cancer", "ls0_"), ("cfg5", "")])
+def test_super_instructions_are_bit_identical_to_the_sequences_they_replace(golden, monkeypatch, cfg, prefix, kind):
+    """rr_plan.cpp close(): the peephole pass (fused pin / constant / column forms, "X; MDOT" carriers), the
+    planned ring rows and the RI_COMBINE points change the instruction stream, not one bit of any reduction.
+    The emulator also checks every data slot and combine point against its own running counts."""
+    if cfg == "cfg5":
+        from rils_rols_b200 import workloads as W
+
+        batch = W.cfg5_neighbourhood().subset(range(0, 600))
+        X, y = W.cfg5_data(257)
+    else:
+        z = golden(cfg)
+        X, y = z["X"], z["y"]
+        batch = B.Batch.load_fields(z, prefix).subset(range(0, 300))
+    if kind == EMU.KIND_EVAL:
+        # EVAL_ONLY wants one program per candidate: score every term as its own candidate
+        progs = [[(batch.code[batch.term_code_begin[t]:batch.term_code_begin[t + 1]], batch.consts)]
+                 for t in range(min(batch.n_terms, 400))]
+        batch = B.Batch.from_programs(B.MODE_EVAL_ONLY, progs)
+    cols = EMU.engine_columns(X, y)
+    fused = EMU.Plan(batch, X.shape[1], kind, tile_cols=40)
+    monkeypatch.setenv("RR_B200_DEBUG_NO_FUSE", "1")
+    monkeypatch.setenv("RR_B200_DEBUG_NO_MDROWS", "1")
+    plain = EMU.Plan(batch, X.shape[1], kind, tile_cols=40)
+    monkeypatch.delenv("RR_B200_DEBUG_NO_FUSE")
+    monkeypatch.delenv("RR_B200_DEBUG_NO_MDROWS")
+    assert fused.n_dots == plain.n_dots and np.array_equal(fused.tab, plain.tab)
+    assert fused.has_rows and not plain.has_rows
+    assert (_opcodes(plain) >= EMU.RI_MULP0).sum() - (_opcodes(plain) >= EMU.RI_FIRST_M).sum() == 0  # no fused register forms
+    n_real = lambda p: int((_opcodes(p) != EMU.RI_NOP).sum())  # dispatches: data slots and padding are not dispatched
+    if kind == EMU.KIND_GRAM:
+        assert n_real(fused) < 0.8 * n_real(plain)
+        assert (fused.ins["w0"] & EMU.RR_THEN_MDOT).astype(bool).sum() > 0
+    with np.errstate(all="ignore"):
+        d_fused, _ = EMU.run(fused, cols)
+        d_plain, _ = EMU.run(plain, cols)
+    assert np.array_equal(d_fused, d_plain, equal_nan=True)
+
+
 @pytest.mark.parametrize("cfg", ["cfg1_toy", "cfg2_diabetes", "cfg3_breast_cancer"])
 def test_eval_plan_reproduces_fitness(golden, cfg):
     z = golden(cfg)

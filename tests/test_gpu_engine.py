@@ -300,3 +300,24 @@ def test_termless_candidates_only():
             r = eng.score(b)
             assert np.allclose(r.coef[:2], y.mean(), rtol=1e-12)
             assert np.allclose(r.ssr[:2], ((y - y.mean()) ** 2).sum(), rtol=1e-10)
+
+
+def test_super_instructions_change_no_bit(golden, monkeypatch):
+    """The planner's peephole pass (rr_plan.cpp close(): fused forms, "X; MDOT" carriers; RR_B200_FUSE=0
+    switches it off) must not change one bit of what the 4-samples-per-thread core returns: same
+    operations, same order, same ring rows. n is chosen so that full tiles (PTX core) and a partial
+    tile (C++ interpreter) both take part."""
+    z = golden("cfg5_neighbourhood")
+    n = 70000 + 123
+    X, y = workloads.cfg5_data(n)
+    sub = B.Batch.load_fields(z).subset(range(0, 700))
+    with Engine(X, y, flags=B.FLAG_FORCE_GRAM) as eng:
+        fused = eng.score(sub)
+        monkeypatch.setenv("RR_B200_FUSE", "0")
+        plain = eng.score(sub)
+        monkeypatch.delenv("RR_B200_FUSE")
+        st = eng.stats()
+    assert st["sweep_launches"] >= 2
+    assert np.array_equal(fused.ssr, plain.ssr, equal_nan=True)
+    assert np.array_equal(fused.coef, plain.coef, equal_nan=True)
+    assert np.array_equal(fused.nonzero_pivots, plain.nonzero_pivots)
