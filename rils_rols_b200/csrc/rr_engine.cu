@@ -183,7 +183,7 @@ struct rr_engine {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t flags = 0;
     int64_t n = 0, ld = 0, n_total = 0;
     int32_t d = 0;
@@ -196,6 +196,7 @@ struct rr_engine {
     void *allreduce_user = nullptr;
     int rank = 0, world = 1;
     // grow-only work buffers
+    DevBuf d_ins2, d_chunks2, d_cols2, d_acc2;  // second sweep in flight (run_gram plans the batch in two halves)
     DevBuf d_ins, d_chunks, d_cols, d_acc, d_dots, d_rdots, d_tab, d_rtab, d_ws, d_wsoff, d_list, d_coef, d_cs,
         d_nzp, d_ssr, d_flags, d_status, d_delta, d_V, d_A, d_rhs, d_aux, d_perm, d_ctb, d_tid, d_misc, d_gather,
         d_t0, d_t1, d_t2, d_t3, d_t4;  // small per-pass tables of the Gram path
@@ -216,7 +217,7 @@ struct rr_engine {
     }
     void free_all()
     {
-        for (DevBuf *b : {&X, &d_ins, &d_chunks, &d_cols, &d_acc, &d_dots, &d_rdots, &d_tab, &d_rtab, &d_ws, &d_wsoff,
+        for (DevBuf *b : {&X, &d_ins2, &d_chunks2, &d_cols2, &d_acc2, &d_ins, &d_chunks, &d_cols, &d_acc, &d_dots, &d_rdots, &d_tab, &d_rtab, &d_ws, &d_wsoff,
                           &d_list, &d_coef, &d_cs, &d_nzp, &d_ssr, &d_flags, &d_status, &d_delta, &d_V, &d_A, &d_rhs,
                           &d_aux, &d_perm, &d_ctb, &d_tid, &d_misc, &d_gather, &d_t0, &d_t1, &d_t2, &d_t3, &d_t4})
             b->release();
@@ -339,8 +340,16 @@ int sweep_gx(rr_engine *e, const SweepCfg &c, bool special, size_t smem, int n_c
 
 // Runs one plan: zero accumulators, launch the interpreter, reduce rows into `dots` (device),
 // all-reduce across ranks when sharded. dd: the plan holds DOTDD reductions only.
-int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf &dots, bool dd, double *stg, int64_t ld_stg)
+// set / dots_off / sync: run_gram plans a large batch in two halves and launches the first while it plans the
+// second, so two sweeps can be in flight: `set` picks the device buffers and the event pair, the reduced dots
+// land at dots + dots_off (the caller has sized `dots` for both: growing it here would drop the first half),
+// and with sync = false the call returns right after the launches (finish_sweep reads the time later).
+int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf &dots, bool dd, double *stg, int64_t ld_stg,
+              int set = 0, size_t dots_off = 0, bool sync = true)
 {
+    DevBuf &d_ins = set ? e->d_ins2 : e->d_ins, &d_chunks = set ? e->d_chunks2 : e->d_chunks;
+    DevBuf &d_cols = set ? e->d_cols2 : e->d_cols, &d_acc = set ? e->d_acc2 : e->d_acc;
+    cudaEvent_t ev0 = e->ev[set ? 4 : 2], ev1 = e->ev[set ? 5 : 3];
     if (P.chunks.empty()) return RR_OK;
     const int T = cfg.T();
     const int NW = cfg.TH / 32;
@@ -367,49 +376,49 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     std::memset(&endi, 0, sizeof(endi));
     ins.resize(P.ins.size() + rr::kInsWindow, endi);
     int rc;
-    if ((rc = upload(e, e->d_ins, ins.data(), ins.size()))) return rc;
-    if ((rc = upload(e, e->d_chunks, P.chunks.data(), P.chunks.size()))) return rc;
-    if ((rc = upload(e, e->d_cols, P.cols.data(), P.cols.size()))) return rc;
+    if ((rc = upload(e, d_ins, ins.data(), ins.size()))) return rc;
+    if ((rc = upload(e, d_chunks, P.chunks.data(), P.chunks.size()))) return rc;
+    if ((rc = upload(e, d_cols, P.cols.data(), P.cols.size()))) return rc;
     if (P.n_dots > 0) {
-        CU(e->d_acc.ensure((size_t)rows * stride * 8));
-        CU(cudaMemsetAsync(e->d_acc.p, 0, (size_t)rows * stride * 8, e->stream));
-        CU(dots.ensure((size_t)stride * 8));
+        CU(d_acc.ensure((size_t)rows * stride * 8));
+        CU(cudaMemsetAsync(d_acc.p, 0, (size_t)rows * stride * 8, e->stream));
+        CU(dots.ensure((dots_off + (size_t)stride) * 8));
     } else {
-        CU(e->d_acc.ensure(64));
+        CU(d_acc.ensure(64));
     }
     rr::SweepArgs a;
     a.X = e->X.as<double>();
     a.ld = e->ld;
     a.n = e->n;
-    a.ins = e->d_ins.as<RRIns>();
-    a.chunks = e->d_chunks.as<RRChunk>();
-    a.cols = e->d_cols.as<int32_t>();
-    a.acc = e->d_acc.as<double>();
+    a.ins = d_ins.as<RRIns>();
+    a.chunks = d_chunks.as<RRChunk>();
+    a.cols = d_cols.as<int32_t>();
+    a.acc = d_acc.as<double>();
     a.acc_stride = stride;
     a.acc_rows_per_block = rpb;
     a.stg = stg;
     a.ld_stg = ld_stg;
     a.n_tiles = n_tiles;
     a.dd_ring = env_int("RR_B200_DD_RING", 1);
-    CU(cudaEventRecord(e->ev[2], e->stream));
+    CU(cudaEventRecord(ev0, e->stream));
     kern<<<dim3(gx, n_chunks), cfg.TH, smem, e->stream>>>(a);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(e->ev[3], e->stream));
+    CU(cudaEventRecord(ev1, e->stream));
     e->stats.sweep_launches++;
     e->stats.kernel_launches++;
     if (P.n_dots > 0) {
         if (!dd) {
-            rr::rr_reduce_rows<<<(P.n_dots + 255) / 256, 256, 0, e->stream>>>(e->d_acc.as<double>(), stride, rows,
-                                                                            P.n_dots, dots.as<double>());
+            rr::rr_reduce_rows<<<(P.n_dots + 255) / 256, 256, 0, e->stream>>>(d_acc.as<double>(), stride, rows,
+                                                                            P.n_dots, dots.as<double>() + dots_off);
         } else {
             rr::rr_reduce_rows_dd<<<(P.n_dots / 2 + 255) / 256, 256, 0, e->stream>>>(
-                e->d_acc.as<double>(), stride, rows, P.n_dots / 2, dots.as<double>());
+                d_acc.as<double>(), stride, rows, P.n_dots / 2, dots.as<double>() + dots_off);
         }
         CU(cudaGetLastError());
         e->stats.kernel_launches++;
         if (e->allreduce && e->world > 1) {
             if (!dd) {
-                if (e->allreduce(dots.p, (size_t)P.n_dots, e->stream, e->allreduce_user))
+                if (e->allreduce(dots.as<double>() + dots_off, (size_t)P.n_dots, e->stream, e->allreduce_user))
                     return e->fail(RR_ERR_COLLECTIVE, "all-reduce hook failed");
             } else {
                 // double-double pairs must not be summed in fp64: gather every rank's pairs with a
@@ -417,25 +426,33 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
                 const size_t len = (size_t)P.n_dots;
                 CU(e->d_gather.ensure(len * e->world * 8));
                 CU(cudaMemsetAsync(e->d_gather.p, 0, len * e->world * 8, e->stream));
-                CU(cudaMemcpyAsync(e->d_gather.as<double>() + len * e->rank, dots.p, len * 8, cudaMemcpyDeviceToDevice,
+                CU(cudaMemcpyAsync(e->d_gather.as<double>() + len * e->rank, dots.as<double>() + dots_off, len * 8, cudaMemcpyDeviceToDevice,
                                    e->stream));
                 if (e->allreduce(e->d_gather.p, len * e->world, e->stream, e->allreduce_user))
                     return e->fail(RR_ERR_COLLECTIVE, "all-reduce hook failed");
                 rr::rr_reduce_rows_dd<<<(P.n_dots / 2 + 255) / 256, 256, 0, e->stream>>>(
-                    e->d_gather.as<double>(), (int64_t)len, e->world, P.n_dots / 2, dots.as<double>());
+                    e->d_gather.as<double>(), (int64_t)len, e->world, P.n_dots / 2, dots.as<double>() + dots_off);
                 CU(cudaGetLastError());
                 e->stats.kernel_launches++;
             }
         }
     }
-    // sweep time is read after the batch's final synchronisation
-    CU(cudaStreamSynchronize(e->stream));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]);
-    e->sweep_ms_accum += ms;
     e->stats.distinct_dots += P.n_dot_ins;
     e->stats.w_shared += P.w_issued;
+    if (!sync) return RR_OK;
+    // sweep time is read after the synchronisation
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    e->sweep_ms_accum += ms;
     return RR_OK;
+}
+
+// after the stream has been synchronised: account the time of a sweep that was launched with sync = false
+void finish_sweep(rr_engine *e, int set)
+{
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev[set ? 4 : 2], e->ev[set ? 5 : 3]) == cudaSuccess) e->sweep_ms_accum += ms;
 }
 
 rr::PlanLimits limits_for(rr_engine *e, const SweepCfg &cfg, int n_cand)
@@ -729,15 +746,54 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     int rc = ensure_result_buffers(e, nc, n_coef);
     if (rc) return rc;
 
-    // pass 1: Gram / A^T yc / column sums, shared across candidates
+    // pass 1: Gram / A^T yc / column sums, shared across candidates.
+    // A large neighbourhood on a large data set is planned in two halves: the sweep of the first half runs
+    // while the host plans the second (planning is serial host work, ~1 us per candidate; with the rows
+    // sharded over several GPUs it is otherwise a visible part of the step). The halves share nothing but the
+    // base solution's terms, which each half evaluates and reduces once (a few dozen instructions).
     rr::SweepPlan P1;
     std::vector<int32_t> tab, tab_begin;
-    std::string err = bp.plan_gram(lim, cols, nullptr, false, P1, tab, tab_begin);
-    if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
-    phase("plan gram");
-    rc = run_sweep(e, P1, S, e->d_dots, false, nullptr, 0);
-    if (rc) return rc;
-    phase("sweep gram");
+    std::string err;
+    const bool pipelined = env_int("RR_B200_PIPELINE", 1) != 0 && nc >= 1024 && S.S == 4 && lim.target_chunks == 1;
+    if (!pipelined) {
+        err = bp.plan_gram(lim, cols, nullptr, false, P1, tab, tab_begin);
+        if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
+        phase("plan gram");
+        rc = run_sweep(e, P1, S, e->d_dots, false, nullptr, 0);
+        if (rc) return rc;
+        phase("sweep gram");
+    } else {
+        // the reduced dots of both halves live in one vector: size it before the first launch
+        size_t tab_total = 0;
+        for (int c = 0; c < nc; ++c) {
+            const size_t m = (size_t)bp.k_of(c) - 1;
+            tab_total += m * (m + 1) / 2 + 2 * m;
+        }
+        CU(e->d_dots.ensure((tab_total + 256) * 8));
+        const int half = nc / 2;
+        std::vector<int32_t> la(half), lb(nc - half);
+        for (int c = 0; c < half; ++c) la[c] = c;
+        for (int c = half; c < nc; ++c) lb[c - half] = c;
+        err = bp.plan_gram(lim, cols, &la, false, P1, tab, tab_begin);
+        if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
+        rc = run_sweep(e, P1, S, e->d_dots, false, nullptr, 0, 0, 0, false);
+        if (rc) return rc;
+        rr::SweepPlan P2;
+        std::vector<int32_t> tab2, tab2_begin;
+        err = bp.plan_gram(lim, cols, &lb, false, P2, tab2, tab2_begin);
+        if (!err.empty()) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, err); }
+        const size_t off2 = (size_t)round_up(std::max(P1.n_dots, 1), 32);
+        if (off2 + (size_t)P2.n_dots > tab_total + 256) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, "internal: dot vector too small"); }
+        rc = run_sweep(e, P2, S, e->d_dots, false, nullptr, 0, 1, off2, false);
+        if (rc) { cudaStreamSynchronize(e->stream); return rc; }
+        const int32_t t0 = (int32_t)tab.size();
+        for (int32_t id : tab2) tab.push_back(id + (int32_t)off2);
+        for (size_t i = 1; i < tab2_begin.size(); ++i) tab_begin.push_back(tab2_begin[i] + t0);
+        CU(cudaStreamSynchronize(e->stream));
+        finish_sweep(e, 0);
+        finish_sweep(e, 1);
+        phase("plan + sweep gram (two halves)");
+    }
 
     // per-candidate solve
     std::vector<int64_t> wsoff(nc + 1, 0);
