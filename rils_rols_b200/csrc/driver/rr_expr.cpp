@@ -1,6 +1,10 @@
 // rr_expr.cpp — see rr_expr.h. Paths in comments are relative to /root/reference/rils_rols_cpp.
 #include "rr_expr.h"
 
+#include <algorithm>
+#include <charconv>
+#include <cstdio>
+
 #include <cmath>
 #include <stdexcept>
 
@@ -57,34 +61,103 @@ int size_of(const Expr &e)
     return 1 + size_of(*e.left) + size_of(*e.right);
 }
 
-std::string to_string(const Expr &e)
+namespace {
+
+void append_int(std::string &s, long long v)
 {
+    char buf[24];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v);
+    s.append(buf, r.ptr);
+}
+
+// std::to_string(double) == printf("%f"): 6 decimals, correctly rounded from the exact binary value. The key of
+// every dedupe set is built from it, so the fast path below must give the same characters: |v| < 10^6 is
+// scaled by 10^6 in fp64 (error < 1.2e-4 of a unit in the last printed digit) and rounded; when the scaled
+// value is within 1e-3 of a rounding boundary - where that error could matter, ties included - and for
+// everything else (large, nan, inf) snprintf decides.
+void append_fixed6(std::string &s, double v)
+{
+    const double a = std::fabs(v);
+    if (a < 1e6) {  // false for nan
+        const double scaled = a * 1e6;
+        const double fl = std::floor(scaled);
+        const double frac = scaled - fl;  // exact
+        if (std::fabs(frac - 0.5) > 1e-3) {
+            const unsigned long long q = (unsigned long long)fl + (frac > 0.5 ? 1u : 0u);
+            if (std::signbit(v)) s.push_back('-');
+            append_int(s, (long long)(q / 1000000u));
+            char d[7];
+            unsigned r = (unsigned)(q % 1000000u);
+            for (int i = 5; i >= 0; --i) {
+                d[i] = (char)('0' + r % 10);
+                r /= 10;
+            }
+            s.push_back('.');
+            s.append(d, 6);
+            return;
+        }
+    }
+    char buf[400];
+    const int n = std::snprintf(buf, sizeof(buf), "%f", v);
+    s.append(buf, (size_t)std::max(0, std::min(n, (int)sizeof(buf) - 1)));
+}
+
+void append_string(const Expr &e, std::string &s)
+{
+    auto bin = [&](const char *open, const char *mid, const char *close) {
+        s += open;
+        append_string(*e.left, s);
+        s += mid;
+        append_string(*e.right, s);
+        s += close;
+    };
+    auto un = [&](const char *open, const char *close) {
+        s += open;
+        append_string(*e.left, s);
+        s += close;
+    };
     switch (e.type) {
     case Op::CONST:
         // near-integers print as ints, everything else with std::to_string's 6 decimals (node.h:257-261)
-        if (std::abs(std::round(e.value) - e.value) < kEps) return std::to_string((int)(std::round(e.value)));
-        return std::to_string(e.value);
-    case Op::VAR: return "x" + std::to_string(e.var);
-    case Op::PLUS: return "(" + to_string(*e.left) + "+" + to_string(*e.right) + ")";
-    case Op::MINUS: return "(" + to_string(*e.left) + "-" + to_string(*e.right) + ")";
-    case Op::MULTIPLY: return "(" + to_string(*e.left) + "*" + to_string(*e.right) + ")";
-    case Op::DIVIDE: return "(" + to_string(*e.left) + "/" + to_string(*e.right) + ")";
-    case Op::SIN: return "sin(" + to_string(*e.left) + ")";
-    case Op::COS: return "cos(" + to_string(*e.left) + ")";
-    case Op::LN: return "ln(" + to_string(*e.left) + ")";
-    case Op::EXP: return "exp(" + to_string(*e.left) + ")";
-    case Op::SQRT: return "sqrt(" + to_string(*e.left) + ")";
-    case Op::SQR: return "((" + to_string(*e.left) + ")**2)";
-    case Op::POW: return "pow(" + to_string(*e.left) + "," + to_string(*e.right) + ")";
+        if (std::abs(std::round(e.value) - e.value) < kEps) append_int(s, (int)(std::round(e.value)));
+        else append_fixed6(s, e.value);
+        return;
+    case Op::VAR:
+        s.push_back('x');
+        append_int(s, e.var);
+        return;
+    case Op::PLUS: return bin("(", "+", ")");
+    case Op::MINUS: return bin("(", "-", ")");
+    case Op::MULTIPLY: return bin("(", "*", ")");
+    case Op::DIVIDE: return bin("(", "/", ")");
+    case Op::SIN: return un("sin(", ")");
+    case Op::COS: return un("cos(", ")");
+    case Op::LN: return un("ln(", ")");
+    case Op::EXP: return un("exp(", ")");
+    case Op::SQRT: return un("sqrt(", ")");
+    case Op::SQR: return un("((", ")**2)");
+    case Op::POW: return bin("pow(", ",", ")");
     // all four comparisons print as '<' (node.h:286-293): they collide in every string-keyed set
     case Op::LESS_THAN:
     case Op::GREATER_THAN:
     case Op::EQUAL:
-    case Op::NOT_EQUAL: return "(" + to_string(*e.left) + "<" + to_string(*e.right) + ")";
-    case Op::MIN: return "MIN(" + to_string(*e.left) + ", " + to_string(*e.right) + ")";
-    case Op::MAX: return "MAX(" + to_string(*e.left) + ", " + to_string(*e.right) + ")";
-    default: return "*****UNKNOWN*****";
+    case Op::NOT_EQUAL: return bin("(", "<", ")");
+    case Op::MIN: return bin("MIN(", ", ", ")");
+    case Op::MAX: return bin("MAX(", ", ", ")");
+    default: s += "*****UNKNOWN*****"; return;
     }
+}
+
+}  // namespace
+
+// one buffer, appended to in place (the recursive concatenation of temporaries this replaces was 40 % of
+// all_candidates)
+std::string to_string(const Expr &e)
+{
+    std::string s;
+    s.reserve(160);
+    append_string(e, s);
+    return s;
 }
 
 bool allowed_left(Op parent, const Expr &child)
