@@ -12,10 +12,11 @@
 //   per sweep.
 //   Reduction partners that many terms share (base-solution terms, centred target) live in 8 per-sample
 //   pin registers; a reduction (RI_MDOT / RI_DOTM) forms the thread's partial over its S samples and
-//   parks it in the warp's shared-memory ring; every 8 reductions the warp transposes the ring and adds
-//   the 8 warp totals with RED.ADD.F64 to the warp's PRIVATE accumulator row in global memory
+//   parks it in the warp's shared-memory ring; every 8 reductions the warp transposes the ring and stages
+//   the 8 warp totals, and every 32 reductions the block's warps add up their staged totals in fixed order
+//   and issue one RED.ADD.F64 per reduction to the BLOCK's accumulator row in global memory
 //   (deterministic: one writer per address, fixed order; details in rr_sweep_core.cuh). Rows are summed
-//   by rr_reduce_rows afterwards.
+//   by rr_reduce_rows afterwards. Double-double plans keep one row per warp instead.
 //
 // Semantics per opcode follow node::evaluate_inner, /root/reference/rils_rols_cpp/node.cpp:23-95
 // (IEEE +,-,*,/ and sqrt are bit-identical to the CPU; sin/cos/log/exp/pow are CUDA libdevice,
