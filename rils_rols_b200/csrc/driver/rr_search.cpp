@@ -315,6 +315,12 @@ std::vector<Expr> Search::all_candidates(const Expr &passed, bool local_search) 
         std::string s = to_string(cand);
         if (seen.insert(std::move(s)).second) all.push_back(std::move(cand));
     };
+    // the whole solution with one subtree replaced: the string decides first, the deep copy is only made for
+    // a tree that has not been seen
+    auto push_unique_copy = [&](const Expr &whole_tree) {
+        std::string s = to_string(whole_tree);
+        if (seen.insert(std::move(s)).second) all.push_back(Expr(whole_tree));
+    };
     auto candidates = [&](const Expr &t) { return local_search ? change_candidates(t) : perturb_candidates(t); };
     const int whole = size_of(*solution);
     std::vector<Expr *> queue{solution.get()};
@@ -328,7 +334,7 @@ std::vector<Expr> Search::all_candidates(const Expr &passed, bool local_search) 
             ExprP keep = std::move(sub.left);
             for (Expr &c : cands) {
                 sub.left = std::make_unique<Expr>(std::move(c));
-                push_unique(Expr(*solution));
+                push_unique_copy(*solution);
             }
             sub.left = std::move(keep);
             queue.push_back(sub.left.get());
@@ -338,7 +344,7 @@ std::vector<Expr> Search::all_candidates(const Expr &passed, bool local_search) 
             ExprP keep = std::move(sub.right);
             for (Expr &c : cands) {
                 sub.right = std::make_unique<Expr>(std::move(c));
-                push_unique(Expr(*solution));
+                push_unique_copy(*solution);
             }
             sub.right = std::move(keep);
             queue.push_back(sub.right.get());
