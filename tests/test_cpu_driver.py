@@ -77,6 +77,25 @@ def test_string_forms():
         assert M.debug_to_string(code, consts) == want
 
 
+def test_constant_formatting_is_printf_exact():
+    """The dedupe key of every candidate prints constants like std::to_string(double) == printf("%f")
+    (node.h:257-261); the driver's fast path must give the same characters, rounding boundaries included."""
+    rng = np.random.default_rng(7)
+    vals = list(rng.uniform(-10, 10, 4000)) + list(rng.uniform(-1e6, 1e6, 2000)) + list(rng.uniform(-1e-3, 1e-3, 2000))
+    k = rng.integers(-10**9, 10**9, 3000)
+    for base in ((k + 0.5) / 1e6, k / 1e6):  # ties of the 6th decimal and exact 6-decimal values, with neighbours
+        vals += list(base) + list(np.nextafter(base, np.inf)) + list(np.nextafter(base, -np.inf))
+    vals += [0.1, 0.2, 0.3, 78.8, 3.31, 1e-7, -1e-7, 5e-7, 999999.9999995, 1e6 + 0.5, -1e6 - 0.25, 1e15 + 0.5, 1e300, -1e300,
+             4.9999995e-7, 2.5e-6, 123456.7890125]
+    code = np.array([B.ins(B.OP_CONST, 0)], dtype=np.uint32)
+    for v in vals:
+        v = float(v)
+        want = str(int(round(v))) if abs(round(v) - v) < 1e-12 and abs(v) < 2**31 else "%f" % v
+        if abs(round(v) - v) < 1e-12 and abs(v) >= 2**31:
+            continue  # (int) of an out-of-range double is undefined in the reference too
+        assert M.debug_to_string(code, np.array([v])) == want, repr(v)
+
+
 def test_rebuild_snaps_coefficients():
     """rils_rols_cpp.cpp:488-517"""
     v = B.Expr.var
