@@ -225,6 +225,67 @@ def test_residual_plan_matches_rebuilt_model(golden, tile_cols):
     assert n_ok > 60
 
 
+def _random_expr(rng, d, depth):
+    """Random tree over all 19 opcodes (constants, variables, unary, binary, the rarely generated ones)."""
+    if depth == 0 or rng.random() < 0.25:
+        return B.Expr.var(int(rng.integers(d))) if rng.random() < 0.6 else B.Expr.const(float(np.round(rng.uniform(-3, 3), 3)))
+    k = int(rng.integers(18))
+    a = _random_expr(rng, d, depth - 1)
+    if k < 6:
+        return [B.sin, B.cos, B.ln, B.exp, B.sqrt, B.sqr][k](a)
+    b = _random_expr(rng, d, depth - 1)
+    if k < 10:
+        return [lambda x, y: x + y, lambda x, y: x - y, lambda x, y: x * y, lambda x, y: x / y][k - 6](a, b)
+    if k < 14:  # multiplications and divisions dominate real neighbourhoods: give the fused forms more chances
+        return a * b if k % 2 else a / b
+    return [B.min_, B.max_, B.eq, lambda x, y: x < y][k - 14](a, b)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("tile_cols", [12, 40])
+def test_super_instructions_on_random_neighbourhoods(monkeypatch, seed, tile_cols):
+    """Fuzz of the peephole pass: neighbourhoods of random candidates that share base terms (so that pins,
+    cache registers, spills and every fused form come into play), planned with and without the pass, must
+    reduce to the same bits; the fused plan must also agree with the design-matrix products."""
+    rng = np.random.default_rng(seed)
+    d, n = 5, 97
+    X = rng.uniform(0.2, 2.5, (n, d))
+    y = rng.normal(size=n)
+    base = [_random_expr(rng, d, 3) for _ in range(5)]
+    cands = []
+    for _ in range(120):
+        terms = list(base)
+        j = int(rng.integers(len(terms)))
+        r = rng.random()
+        if r < 0.4:
+            terms[j] = _random_expr(rng, d, 4)
+        elif r < 0.7:
+            terms[j] = terms[j] * B.Expr.var(int(rng.integers(d))) if rng.random() < 0.5 else terms[j] / B.Expr.var(int(rng.integers(d)))
+        elif r < 0.85:
+            terms[j] = B.Expr.const(float(np.round(rng.uniform(-2, 2), 2))) * terms[j]
+        else:
+            terms.append(_random_expr(rng, d, 2))
+        cands.append(terms)
+    batch = B.Batch.from_exprs(B.MODE_OLS_FIT, cands)
+    cols = EMU.engine_columns(X, y)
+    fused = EMU.Plan(batch, d, EMU.KIND_GRAM, tile_cols=tile_cols)
+    monkeypatch.setenv("RR_B200_DEBUG_NO_FUSE", "1")
+    plain = EMU.Plan(batch, d, EMU.KIND_GRAM, tile_cols=tile_cols)
+    monkeypatch.delenv("RR_B200_DEBUG_NO_FUSE")
+    assert int((_opcodes(fused) != EMU.RI_NOP).sum()) < int((_opcodes(plain) != EMU.RI_NOP).sum())
+    with np.errstate(all="ignore"):
+        d_fused, _ = EMU.run(fused, cols)
+        d_plain, _ = EMU.run(plain, cols)
+        assert np.array_equal(d_fused, d_plain, equal_nan=True)
+        Xfm = O.feature_major(X)
+        for c in range(0, batch.n_cand, 5):
+            A = design(Xfm, batch, c)
+            G, _ = gram_from_dots(fused, d_fused, batch, c, n)
+            want = A.T @ A
+            ok = np.isclose(G, want, rtol=1e-11, atol=0, equal_nan=True) | (~np.isfinite(want) & ~np.isfinite(G))
+            assert ok.all(), f"cand {c}"
+
+
 def test_planner_rejects_malformed_batches():
     good = B.Batch.from_exprs(B.MODE_OLS_FIT, [[B.Expr.var(0) * B.Expr.var(1)]])
     EMU.Plan(good, 2, EMU.KIND_GRAM)
