@@ -211,7 +211,12 @@ class Engine:
                 ext = torch.cuda.ExternalStream(stream, device=dev)
                 with torch.cuda.stream(ext):
                     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-                ext.synchronize()
+                # The collective is stream-ordered already; waiting here makes the host wait for the sweep in
+                # front of it, which serialises run_gram's two-half planning pipeline when rows are sharded.
+                # RR_B200_HOOK_ASYNC=1 leaves it asynchronous (to be validated on >= 2 GPUs before it
+                # becomes the default).
+                if os.environ.get("RR_B200_HOOK_ASYNC", "0") in ("", "0"):
+                    ext.synchronize()
                 return 0
             except Exception as ex:  # pragma: no cover - surfaced as RR_ERR_COLLECTIVE
                 print(f"[rils_rols_b200] all-reduce hook failed: {ex!r}", flush=True)
