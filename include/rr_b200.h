@@ -243,6 +243,10 @@ RR_API int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kind, i
                                int32_t max_slots, int32_t target_chunks, int32_t no_cse, int32_t n_pins,
                                const double *coef_snapped, rr_debug_plan *out);
 RR_API void rr_debug_plan_free(rr_debug_plan *p);
+/* Host-only test hook: the two halves of a batch planned on two threads at once must equal the halves planned
+ * one after the other (rr_score_batch plans the second half of a large neighbourhood on a helper thread).
+ * 0 = identical, 1 = different, RR_ERR_INVALID = malformed batch. */
+RR_API int rr_debug_plan_concurrency_check(const rr_batch *batch, int32_t d, int32_t tile_cols);
 
 /* Last error text: of the engine, or of the calling thread when e == NULL. */
 RR_API const char *rr_last_error(const rr_engine *e);

@@ -18,6 +18,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rr_b200.h"
@@ -747,9 +748,9 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     if (rc) return rc;
 
     // pass 1: Gram / A^T yc / column sums, shared across candidates.
-    // A large neighbourhood on a large data set is planned in two halves: the sweep of the first half runs
-    // while the host plans the second (planning is serial host work, ~1 us per candidate; with the rows
-    // sharded over several GPUs it is otherwise a visible part of the step). The halves share nothing but the
+    // A large neighbourhood on a large data set is planned in two halves, the second on a helper thread: its
+    // planning overlaps the first half's planning, launch and sweep (planning is host work, ~1 us per
+    // candidate; with the rows sharded over several GPUs it is otherwise a visible part of the step). The halves share nothing but the
     // base solution's terms, which each half evaluates and reduces once (a few dozen instructions).
     rr::SweepPlan P1;
     std::vector<int32_t> tab, tab_begin;
@@ -774,14 +775,37 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         std::vector<int32_t> la(half), lb(nc - half);
         for (int c = 0; c < half; ++c) la[c] = c;
         for (int c = half; c < nc; ++c) lb[c - half] = c;
-        err = bp.plan_gram(lim, cols, &la, false, P1, tab, tab_begin);
-        if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
-        rc = run_sweep(e, P1, S, e->d_dots, false, nullptr, 0, 0, 0, false);
-        if (rc) return rc;
+        // the second half is planned on a helper thread (plan_gram only reads the analysed batch): it overlaps
+        // the first half's planning and launch, and - when an all-reduce hook blocks this thread until the
+        // first sweep is done - the first sweep as well
         rr::SweepPlan P2;
         std::vector<int32_t> tab2, tab2_begin;
-        err = bp.plan_gram(lim, cols, &lb, false, P2, tab2, tab2_begin);
-        if (!err.empty()) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, err); }
+        std::string err2;
+        auto plan_second = [&]() { err2 = bp.plan_gram(lim, cols, &lb, false, P2, tab2, tab2_begin); };
+        std::thread planner2;
+        struct Joiner {  // whatever path leaves this scope, the helper is joined first (it writes to the locals above)
+            std::thread &t;
+            ~Joiner()
+            {
+                if (t.joinable()) t.join();
+            }
+        } joiner{planner2};
+        bool threaded = true;
+        try {
+            planner2 = std::thread(plan_second);
+        } catch (...) {
+            threaded = false;  // no thread to be had: plan the second half here, after the first launch
+        }
+        err = bp.plan_gram(lim, cols, &la, false, P1, tab, tab_begin);
+        if (!err.empty()) {
+            if (threaded) planner2.join();
+            return e->fail(RR_ERR_INVALID, err);
+        }
+        rc = run_sweep(e, P1, S, e->d_dots, false, nullptr, 0, 0, 0, false);
+        if (threaded) planner2.join();
+        else if (!rc) plan_second();
+        if (rc) { cudaStreamSynchronize(e->stream); return rc; }
+        if (!err2.empty()) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, err2); }
         const size_t off2 = (size_t)round_up(std::max(P1.n_dots, 1), 32);
         if (off2 + (size_t)P2.n_dots > tab_total + 256) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, "internal: dot vector too small"); }
         rc = run_sweep(e, P2, S, e->d_dots, false, nullptr, 0, 1, off2, false);

@@ -1460,6 +1460,7 @@ std::string BatchPlanner::plan_materialise(const PlanLimits &lim, const ColIds &
 // host-only tooling entry points (include/rr_b200.h)
 // ---------------------------------------------------------------------------------------------
 #include <cstdlib>
+#include <thread>
 
 namespace {
 template <typename T> T *dup_vec(const std::vector<T> &v)
@@ -1528,6 +1529,43 @@ extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kin
     out->w_issued = P.w_issued;
     out->w_contract = bp.w_contract();
     return RR_OK;
+}
+
+// Test hook (host only): plan_gram of the two halves of a batch on two threads at once and one after the
+// other must give the same instruction streams and tables (run_gram plans its second half on a helper thread).
+// Returns 0 when they agree, 1 when they differ, RR_ERR_INVALID on a malformed batch.
+extern "C" int rr_debug_plan_concurrency_check(const rr_batch *batch, int32_t d, int32_t tile_cols)
+{
+    if (!batch || batch->n_cand < 2) return RR_ERR_INVALID;
+    rr::BatchPlanner bp(batch, d);
+    if (!bp.analyse(false).empty()) return RR_ERR_INVALID;
+    rr::PlanLimits lim;
+    lim.tile_cols = tile_cols;
+    lim.mdot_rows = true;
+    rr::ColIds cols{d, d + 1};
+    const int32_t half = batch->n_cand / 2;
+    std::vector<int32_t> la(half), lb(batch->n_cand - half);
+    for (int32_t c = 0; c < half; ++c) la[c] = c;
+    for (int32_t c = half; c < batch->n_cand; ++c) lb[c - half] = c;
+    struct Out {
+        rr::SweepPlan P;
+        std::vector<int32_t> tab, tab_begin;
+        std::string err;
+    } seq[2], par[2];
+    seq[0].err = bp.plan_gram(lim, cols, &la, false, seq[0].P, seq[0].tab, seq[0].tab_begin);
+    seq[1].err = bp.plan_gram(lim, cols, &lb, false, seq[1].P, seq[1].tab, seq[1].tab_begin);
+    std::thread t([&]() { par[1].err = bp.plan_gram(lim, cols, &lb, false, par[1].P, par[1].tab, par[1].tab_begin); });
+    par[0].err = bp.plan_gram(lim, cols, &la, false, par[0].P, par[0].tab, par[0].tab_begin);
+    t.join();
+    for (int h = 0; h < 2; ++h) {
+        if (!seq[h].err.empty() || !par[h].err.empty()) return RR_ERR_INVALID;
+        if (seq[h].P.ins.size() != par[h].P.ins.size() || seq[h].tab != par[h].tab || seq[h].tab_begin != par[h].tab_begin ||
+            seq[h].P.n_dots != par[h].P.n_dots)
+            return 1;
+        if (!seq[h].P.ins.empty() && std::memcmp(seq[h].P.ins.data(), par[h].P.ins.data(), seq[h].P.ins.size() * sizeof(RRIns)) != 0)
+            return 1;
+    }
+    return 0;
 }
 
 extern "C" void rr_debug_plan_free(rr_debug_plan *p)

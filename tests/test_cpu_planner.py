@@ -286,6 +286,24 @@ def test_super_instructions_on_random_neighbourhoods(monkeypatch, seed, tile_col
             assert ok.all(), f"cand {c}"
 
 
+def test_halves_planned_concurrently_equal_halves_planned_in_turn():
+    """rr_engine.cu run_gram plans the second half of a large neighbourhood on a helper thread: plan_gram must
+    be re-entrant (it only reads the analysed batch)."""
+    import ctypes as C
+
+    from rils_rols_b200 import workloads as W
+
+    L = E.lib()
+    L.rr_debug_plan_concurrency_check.argtypes = [C.POINTER(B.rr_batch), C.c_int32, C.c_int32]
+    L.rr_debug_plan_concurrency_check.restype = C.c_int
+    nb = W.cfg5_neighbourhood()
+    for lo, hi in ((0, 4096), (100, 1300), (2000, 2100)):
+        sub = nb.subset(range(lo, hi))
+        bs = sub.as_struct()
+        for _ in range(3):
+            assert L.rr_debug_plan_concurrency_check(C.byref(bs), 20, 23) == 0
+
+
 def test_planner_rejects_malformed_batches():
     good = B.Batch.from_exprs(B.MODE_OLS_FIT, [[B.Expr.var(0) * B.Expr.var(1)]])
     EMU.Plan(good, 2, EMU.KIND_GRAM)
