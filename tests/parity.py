@@ -14,9 +14,13 @@ fp64. What "relative" is measured against is written here once:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from rils_rols_b200 import batch as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 REL = 1e-9
 KAPPA_MAX = 1e6

@@ -10,7 +10,9 @@ import pytest
 from oracle import pyoracle as O
 from rils_rols_b200 import batch as B
 
-from rils_rols_b200 import rils_rols_cpp as M  # noqa: E402
+import rils_rols_b200  # noqa: E402
+
+M = rils_rols_b200.driver_module()
 
 
 def expr_from_postfix(code, consts) -> B.Expr:
@@ -140,3 +142,37 @@ def test_candidate_generation_matches_reference_on_random_walks(classification, 
         code, consts = nxt[0], nxt[1]
         steps += 1
     assert steps == 7
+
+
+def test_reference_front_end_binds_this_module_unmodified():
+    """the reference's Python front end stays unchanged and must keep working
+    against the new module. Import it as it is (rils_rols/rils_rols.py:8 does `import rils_rols_cpp`) and
+    check that it bound the module built here and that its estimators construct the drop-in class with the
+    reference's positional signature (rils_rols_cpp.cpp:1000). fit() itself needs the GPU: tests/test_gpu_fit.py."""
+    import hashlib
+    import importlib
+
+    ref_root = os.environ.get("RR_REFERENCE", "/root/reference")
+    installed = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    base = next((b for b in (ref_root, installed) if os.path.isfile(os.path.join(b, "rils_rols", "rils_rols.py"))), None)
+    if base is None:
+        pytest.skip("reference Python package not available")
+    if base not in sys.path:
+        sys.path.append(base)
+    fe = importlib.import_module("rils_rols.rils_rols")
+    assert fe.rils_rols_cpp is M
+    if base == installed and os.path.isdir(ref_root):
+        for f in ("rils_rols.py", "utils.py", "__init__.py"):  # the installed copy is the reference's file, byte for byte
+            a = hashlib.sha256(open(os.path.join(ref_root, "rils_rols", f), "rb").read()).hexdigest()
+            b = hashlib.sha256(open(os.path.join(installed, "rils_rols", f), "rb").read()).hexdigest()
+            assert a == b, f
+    reg = fe.RILSROLSRegressor(max_fit_calls=10, max_time=1, random_state=3)
+    clf = fe.RILSROLSBinaryClassifier(max_fit_calls=10, max_time=1, random_state=3)
+    assert reg.classification is False and clf.classification is True
+    # what fit_inner does at rils_rols.py:100 (positional pybind constructor)
+    obj = fe.rils_rols_cpp.rils_rols(reg.classification, reg.max_fit_calls, reg.max_time, reg.complexity_penalty,
+                                     reg.max_complexity, reg.sample_size, reg.verbose, reg.random_state)
+    for name in ("fit", "predict", "get_model_string", "get_best_time", "get_fit_calls", "get_total_time"):
+        assert callable(getattr(obj, name))
+    with pytest.raises(Exception, match="not build yet"):
+        reg.predict([[1.0, 2.0]])

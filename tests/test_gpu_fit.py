@@ -45,7 +45,9 @@ def add_pareto(pareto, f):
 @pytest.mark.parametrize("cfg,classification,max_complexity,calls", [
     ("cfg1_toy", False, 50, 6000), ("cfg2_diabetes", False, 20, 6000), ("cfg3_breast_cancer", True, 20, 8000)])
 def test_shadow_replay_of_search_decisions(cfg, classification, max_complexity, calls):
-    from rils_rols_b200 import rils_rols_cpp as M
+    import rils_rols_b200
+
+    M = rils_rols_b200.driver_module()
 
     X, y = workloads.config_data(cfg)
     n, d = X.shape
@@ -128,12 +130,33 @@ def test_shadow_replay_of_search_decisions(cfg, classification, max_complexity, 
     assert stats["ambiguous_decisions"] <= 0.15 * stats["decisions"]
 
 
-def test_readme_toy_problem_recovers_ground_truth_function():
-    """BASELINE config 1 (test_example.py:18-32), shorter budget: the four ground-truth terms."""
-    from rils_rols_b200.rils_rols import RILSROLSRegressor
+def reference_front_end():
+    """The reference's own sklearn-style front end, UNMODIFIED (rils_rols/rils_rols.py:16-188), bound to
+    this repo's `rils_rols_cpp` module: taken from $RR_REFERENCE or /root/reference where that exists, else
+    from the copy `make -C oracle ref` installs into oracle/_ref (git-ignored; it travels to the GPU box
+    with the built reference module). Skips when neither is there."""
+    import importlib
 
+    import rils_rols_b200
+
+    M = rils_rols_b200.driver_module()  # puts rils_rols_b200/ on sys.path: `import rils_rols_cpp` finds it
+    for base in (os.environ.get("RR_REFERENCE", "/root/reference"), os.path.join(parity.ROOT, "oracle", "_ref")):
+        if os.path.isfile(os.path.join(base, "rils_rols", "rils_rols.py")):
+            if base not in sys.path:
+                sys.path.append(base)
+            fe = importlib.import_module("rils_rols.rils_rols")
+            assert fe.rils_rols_cpp is M, "the front end bound another rils_rols_cpp"
+            assert os.path.dirname(os.path.abspath(fe.__file__)) == os.path.join(base, "rils_rols")
+            return fe
+    pytest.skip("the reference's Python package is not available (build oracle/_ref where /root/reference exists)")
+
+
+def test_reference_front_end_regressor_on_readme_toy_problem():
+    """BASELINE config 1 (test_example.py:18-32) through the reference's unmodified RILSROLSRegressor,
+    shorter budget: the four ground-truth terms."""
+    fe = reference_front_end()
     Xtr, ytr, Xte, yte = workloads.config_data("cfg1_toy", test=True)
-    reg = RILSROLSRegressor(sample_size=1, random_state=12345, max_fit_calls=30000, max_time=300)
+    reg = fe.RILSROLSRegressor(sample_size=1, random_state=12345, max_fit_calls=30000, max_time=300)
     reg.fit(Xtr, ytr)
     assert reg.fit_calls in (30000, 30001)
     r2_tr, r2_te = reg.score(Xtr, ytr), reg.score(Xte, yte)
@@ -142,11 +165,10 @@ def test_readme_toy_problem_recovers_ground_truth_function():
     assert "maxFitCalls=30000" in reg.fit_report_string()
 
 
-def test_classifier_front_end():
-    from rils_rols_b200.rils_rols import RILSROLSBinaryClassifier
-
+def test_reference_front_end_classifier():
+    fe = reference_front_end()
     Xtr, ytr, Xte, yte = workloads.config_data("cfg3_breast_cancer", test=True)
-    clf = RILSROLSBinaryClassifier(sample_size=1, max_complexity=20, random_state=12345, max_fit_calls=8000, max_time=300)
+    clf = fe.RILSROLSBinaryClassifier(sample_size=1, max_complexity=20, random_state=12345, max_fit_calls=8000, max_time=300)
     clf.fit(Xtr, ytr)
     acc_tr, acc_te = clf.score(Xtr, ytr), clf.score(Xte, yte)
     print(f"\nbreast cancer: model {clf.model_string()} acc train {acc_tr} test {acc_te}")
@@ -157,9 +179,29 @@ def test_classifier_front_end():
         clf.fit(Xtr, ytr + 1)
 
 
+def test_module_boundary_without_front_end():
+    """The pybind11 boundary itself (rils_rols_cpp.cpp:998-1007): constructor signature, fit / predict /
+    getters, the size-mismatch error, thresholded predictions of a classifier."""
+    import rils_rols_b200
+
+    M = rils_rols_b200.driver_module()
+    Xtr, ytr, Xte, yte = workloads.config_data("cfg3_breast_cancer", test=True)
+    rr = M.rils_rols(True, 3000, 300, PENALTY, 20, 1.0, False, 12345)
+    with pytest.raises(ValueError):
+        rr.fit(Xtr.reshape(-1, 1), ytr, Xtr.shape[0] + 1, Xtr.shape[1])
+    rr.fit(Xtr.reshape(-1, 1), ytr, Xtr.shape[0], Xtr.shape[1])
+    assert rr.get_fit_calls() in (3000, 3001) and rr.get_total_time() > 0 and rr.get_best_time() >= 0
+    assert isinstance(rr.get_model_string(), str) and rr.get_model_string()
+    yp = rr.predict(Xte.reshape(-1, 1), Xte.shape[0], Xte.shape[1])
+    assert yp.shape == (Xte.shape[0],) and set(np.unique(yp)) <= {0.0, 1.0}
+    assert (yp == yte).mean() > 0.85
+
+
 def test_large_n_fit_config4_style():
     """BASELINE config 4 (test_large.py style): 1M x 10 synthetic, sample_size=1: Gram path."""
-    from rils_rols_b200 import rils_rols_cpp as M
+    import rils_rols_b200
+
+    M = rils_rols_b200.driver_module()
 
     X, y = workloads.cfg4_data(1_000_000, 10)
     rr = M.rils_rols(False, 20000, 600, PENALTY, 50, 1.0, False, 12345)

@@ -11,7 +11,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rils_rols_b200 import workloads  # noqa: E402
-from rils_rols_b200 import rils_rols_cpp as M  # noqa: E402
+import rils_rols_b200  # noqa: E402
+
+M = rils_rols_b200.driver_module()
 
 try:
     from oracle import pyoracle as O

@@ -12,7 +12,9 @@ code = r'''
 import sys, time; sys.path.insert(0, %r)
 import numpy as np
 from rils_rols_b200 import workloads
-from rils_rols_b200 import rils_rols_cpp as M
+import rils_rols_b200
+
+M = rils_rols_b200.driver_module()
 name = sys.argv[1]
 X, y = workloads.config_data(name)
 rr = M.rils_rols(name == "cfg3_breast_cancer", 100000, 100000, 0.001, 20, 1.0, False, 12345)
