@@ -101,6 +101,115 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
 
 
+
+# well-conditioned candidates of the committed neighbourhood (reference full rank, kappa <= 1e4 at n = 4096):
+# the ones the after-run check compares with the C oracle on ALL benchmark rows
+PARITY_CANDS = [37, 220, 403, 586, 769, 952, 1135, 1318, 1501, 1684, 1867, 2050, 2233, 2416, 2599, 2843]
+REL = 1e-9
+
+
+def parity_block(batch: B.Batch, res: B.Result, X, y, sst: float, n_total: int, unsharded=None):
+    """After the timed region, outside every timer: (1) PARITY_CANDS of the result the timed steps produced against
+    the C restatement of the reference (oracle/rr_oracle.c, pinned bit-for-bit on the unmodified reference) run on all
+    n_total rows; (2) for N > 1 every candidate of the sample-sharded result against an unsharded engine holding
+    all rows on rank 0's GPU. Errors as in tests/parity.py: coefficients relative to the candidate's largest,
+    fitness (1-R2, RMSE) relative with an absolute floor of 1e-12."""
+    from oracle import pyoracle as O
+
+    t0 = time.perf_counter()
+    sub = batch.subset(PARITY_CANDS)
+    ores, of0, of1, ofs = O.score_batch(O.feature_major(X), y, sub)
+    yscale = float(np.sqrt(sst / n_total))
+    max_coef = max_fit = 0.0
+    for j, c in enumerate(PARITY_CANDS):
+        cr, cg = ores.coef[sub.coef_slice(j)], res.coef[batch.coef_slice(c)]
+        max_coef = max(max_coef, float(np.max(np.abs(cg - cr)) / max(np.max(np.abs(cr)), 1e-300)))
+        g0, g1, _ = B.fitness_tuple(res.ssr[c], sst, n_total, 0)
+        max_fit = max(max_fit, abs(g0 - of0[j]) / (abs(of0[j]) + 1e-12 / REL), abs(g1 - of1[j]) / (abs(of1[j]) + 1e-12 * yscale / REL))
+    out = {"oracle": f"oracle/rr_oracle.c on all {n_total} rows", "n_checked": len(PARITY_CANDS), "candidates": PARITY_CANDS,
+           "max_coef_err": max_coef, "max_fit_err": max_fit, "max_err": max(max_coef, max_fit), "tolerance": REL,
+           "oracle_s": time.perf_counter() - t0}
+    if unsharded is not None:
+        fin = np.isfinite(unsharded.ssr) & np.isfinite(res.ssr)
+        ssr_err = float(np.max(np.abs(res.ssr[fin] - unsharded.ssr[fin]) / (np.abs(unsharded.ssr[fin]) + 1e-12 * sst / REL))) if fin.any() else 0.0
+        coef_err, n_coef_checked = 0.0, 0
+        for c in range(batch.n_cand):
+            a, b = res.coef[batch.coef_slice(c)], unsharded.coef[batch.coef_slice(c)]
+            # well-posed by the engine's own account: no rank deficiency, no escalation, moderate coefficients
+            if (unsharded.flags[c] | res.flags[c]) & (B.RES_RANKDEF | B.RES_DD | B.RES_NONFINITE) or not np.all(np.isfinite(b)) or np.max(np.abs(b)) >= 1e8:
+                continue
+            coef_err = max(coef_err, float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)))
+            n_coef_checked += 1
+        out["vs_unsharded"] = {"n_cand": batch.n_cand, "max_ssr_err": ssr_err, "same_nonfinite": bool(np.array_equal(np.isfinite(res.ssr), np.isfinite(unsharded.ssr))),
+                               "max_coef_err": coef_err, "n_coef_checked": n_coef_checked}
+        out["max_err"] = max(out["max_err"], ssr_err, coef_err)
+    return out
+
+
+def hbm_single(eng, info, peaks, peak_src, steps: int = 5):
+    """the HBM-bound regime - ONE program scored EVAL_ONLY over all rows of this GPU (what
+    score_single / tune_single of a large-n fit() do hundreds of times, rils_rols_cpp.cpp:606-607,631,842).
+    Algorithmic bytes = 8 n (distinct variables + 1); time = the interpreter launch (CUDA events on the engine stream)."""
+    v = B.Expr.var
+    progs = {
+        "3 vars": B.sin(v(0)) + v(1) * v(2),
+        "8 vars": ((v(0) + v(1)) + (v(2) * v(3))) + ((v(4) - v(5)) + (v(6) * v(7))),
+    }
+    out = {}
+    for name, e in progs.items():
+        b = B.Batch.from_exprs(B.MODE_EVAL_ONLY, [[e]])
+        r = B.Result.alloc(b)
+        nv = len({int(w >> 8) for w in b.code.tolist() if (w & 0xFF) == B.OP_VAR})
+        for _ in range(2):
+            eng.score(b, r)
+        ms = 0.0
+        for _ in range(steps):
+            eng.score(b, r)
+            ms += eng.stats()["last_sweep_ms"]
+        ms /= steps
+        bytes_ = 8.0 * info.n * (nv + 1)
+        out[name] = {"achieved": bytes_ / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": bytes_ / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": bytes_, "sweep_ms": ms,
+                     "peak_source": peak_src}
+    return out
+
+
+def fit_leg(calls: int, with_reference: bool):
+    """fit() wall time of BASELINE configs 1-4 (test_example.py:18-57; config 4 = 10^6 x 10) through the
+    pybind11 boundary (rils_rols_cpp.rils_rols: the call the reference's front end makes, rils_rols.py:100-107), and the
+    unmodified reference (oracle/_ref, one host core: it is single-threaded) in the same run. Config 4's reference
+    budget is bounded (about 10 s: ~120 fit calls), its rate is what is compared."""
+    import rils_rols_b200
+
+    M = rils_rols_b200.driver_module()
+    R = None
+    if with_reference:
+        from oracle import pyoracle as O
+
+        R = O.load_ref()
+    out = {}
+    for name, cls, mc, ncalls in (("cfg1_toy", False, 50, calls), ("cfg2_diabetes", False, 20, calls),
+                                  ("cfg3_breast_cancer", True, 20, calls), ("cfg4_1Mx10", False, 50, calls)):
+        X, y = workloads.cfg4_data(1_000_000, 10) if name.startswith("cfg4") else workloads.config_data(name)
+        rr = M.rils_rols(cls, ncalls, 100000, 0.001, mc, 1.0, False, 12345)
+        t = time.perf_counter()
+        rr.fit(X.reshape(-1, 1), y, X.shape[0], X.shape[1])
+        wall = time.perf_counter() - t
+        rec = {"n": int(X.shape[0]), "d": int(X.shape[1]), "fit_calls": int(rr.get_fit_calls()), "fit_wall_s": wall,
+               "total_time_s": rr.get_total_time(), "model": rr.get_model_string()}
+        if R is not None:
+            rcalls = ncalls if not name.startswith("cfg4") else 120
+            ref = R.rils_rols(cls, rcalls, 100000, 0.001, mc, 1.0, False, 12345)
+            t = time.perf_counter()
+            ref.fit(X.reshape(-1, 1), y, X.shape[0], X.shape[1])
+            rwall = time.perf_counter() - t
+            rec["reference"] = {"fit_calls": int(ref.get_fit_calls()), "fit_wall_s": rwall, "cores": 1,
+                                "calls_per_s": ref.get_fit_calls() / rwall}
+            rec["calls_per_s"] = rr.get_fit_calls() / wall
+        out[name] = rec
+    return out
+
+
 def reference_trees(R, n_cand: int):
     """The candidate TREES behind the committed batch: all_candidates(tuned_base, local_search=true)
     of the unmodified reference, filtered to <= 50 term nodes exactly like tests/golden/make_golden.py."""
@@ -158,7 +267,9 @@ def run_reference(args):
     X, y = workloads.cfg5_data(max(rows, 1 << 16))
     X, y = X[:rows], y[:rows]
     R = O.load_ref()
-    cores = os.cpu_count() or 1
+    # pinned, so that the ratio does not follow the box's core count: --ref-threads (default 16) replicas, never more
+    # than the host has
+    cores = max(1, min(args.ref_threads, os.cpu_count() or 1))
     if R is not None:
         kind = "reference"
         h = R.RefHarness(False, 0.001, 50, 12345)
@@ -191,7 +302,8 @@ def run_reference(args):
         "config": {"workload": f"cfg5: 4096-candidate LS neighbourhood (OLS_FIT) x {rows}-sample slice of the 2^24 x 20 set",
                    "n_cand": batch.n_cand, "n": rows, "d": 20},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"each step = all {batch.n_cand} candidates x {rows} samples, {cores} replicas of the single-threaded reference"},
+                         "sample": f"each step = all {batch.n_cand} candidates x {rows} samples, {cores} replicas of the single-threaded reference (pinned by --ref-threads; host has {os.cpu_count()} cpus)",
+                         "host_cpus": os.cpu_count(), "threads_pinned": cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -208,6 +320,10 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=16384, help="--impl reference: samples per step")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-threads", type=int, default=16, help="--impl reference: replicas of the single-threaded reference")
+    ap.add_argument("--no-parity", action="store_true", help="skip the after-run parity block (oracle on all rows: ~30 s)")
+    ap.add_argument("--no-fit", action="store_true", help="skip the fit() wall-time leg (BASELINE configs 1-4, N = 1 only: ~40 s)")
+    ap.add_argument("--fit-calls", type=int, default=100000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,7 +353,11 @@ def main():
     torch.cuda.synchronize(dev)
     ingest_s = time.perf_counter() - t0
     if world > 1:
-        eng.set_allreduce_torch()
+        # NCCL inside the engine: torch.distributed only carries the 128-byte unique id to the other ranks
+        if os.environ.get("RR_B200_BENCH_HOOK", "0") not in ("", "0"):
+            eng.set_allreduce_torch()  # the round-1 path (Python callback per all-reduce), kept for comparison
+        else:
+            eng.comm_init_torch()
     info = eng.info()
 
     def barrier():
@@ -291,7 +411,7 @@ def main():
             "config": {"workload": "cfg5: 4096-candidate LS neighbourhood (<= 50 term nodes), OLS_FIT, n=2^24 x d=20, sample-sharded",
                        "n_cand": batch.n_cand, "n": int(info.n_total), "d": int(info.d), "rows_per_gpu": int(info.n),
                        "l2": "inputs_exceed_l2 (2.8 GB of X,y per sweep vs 126 MB L2)", "parallelism": f"sample-shard x{world}",
-                       "ingest_s": ingest_s},
+                       "ingest_s": ingest_s, "ingest_note": "X is resident after rr_engine_create (fit once, score many); its upload + device-side transpose is this one-off cost, outside the timed steps"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": wall_ms / args.steps},
             "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
@@ -309,10 +429,21 @@ def main():
                         "algorithmic_bytes_per_sweep": hbm_bytes},
             },
             "engine": {k: st1[k] for k in ("refined", "exact", "dd", "nonfinite", "distinct_terms", "term_instances",
-                                           "distinct_dots", "dot_instances", "sweep_launches")},
+                                           "distinct_dots", "dot_instances", "sweep_launches", "collectives")},
+            "non_sweep_ms_per_step": (wall_ms - sweep_ms) / args.steps,
         }
+        line["roofline"]["hbm_single"] = hbm_single(eng, info, peaks, peak_src)
+        if not args.no_parity:
+            unsharded = None
+            if world > 1:
+                # all rows on this rank's GPU (2.95 GB), no hook: the unsharded answer to the same batch
+                with Engine(X, y, rowmajor=True, device=local, flags=args.flags) as full:
+                    unsharded = full.score(batch)
+            line["parity"] = parity_block(batch, res, X, y, float(info.sst), int(info.n_total), unsharded)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(batch, X, y)
+        if world == 1 and not args.no_fit:
+            line["fit_wall_s"] = fit_leg(args.fit_calls, with_reference=True)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RR_ABI_VERSION 1
+#define RR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RR_API __attribute__((visibility("default")))
@@ -97,7 +97,8 @@ enum rr_engine_flags {
     RR_FLAG_FORCE_GRAM = 1u << 0,  /* always Gram + Cholesky (+ refinement / dd escalation) */
     RR_FLAG_FORCE_EXACT = 1u << 1, /* always materialise A and run column-pivoted Householder QR */
     RR_FLAG_NO_CSE = 1u << 2,      /* plan every candidate independently (no cross-candidate sharing) */
-    RR_FLAG_X_DEVICE = 1u << 3     /* X / y pointers passed to rr_engine_create are device pointers */
+    RR_FLAG_X_DEVICE = 1u << 3,    /* X / y pointers passed to rr_engine_create are device pointers */
+    RR_FLAG_X_ROWMAJOR = 1u << 4   /* rr_engine_create_sharded: X is row-major n x d (the numpy layout of the pybind boundary) */
 };
 
 /* per-candidate result flags */
@@ -120,7 +121,7 @@ typedef struct rr_batch {
     const uint32_t *code;           /* postfix words, RR_INS(op,arg) */
     const double *consts;           /* constant pool */
     int32_t n_consts;
-    int32_t reserved;
+    int32_t n_code;                 /* words in code[] (ABI 2; 0 = unknown: offsets are then only checked for monotony) */
 } rr_batch;
 
 /*
@@ -144,7 +145,7 @@ typedef struct rr_result {
 } rr_result;
 
 typedef struct rr_engine_info {
-    int64_t n;      /* samples held by THIS engine (its shard) */
+    int64_t n;      /* samples held by THIS engine (its shard; all shards of a single-process multi-GPU engine) */
     int64_t n_total;/* samples over all ranks (== n without an all-reduce hook) */
     int32_t d;
     int32_t device; /* CUDA device ordinal */
@@ -152,6 +153,8 @@ typedef struct rr_engine_info {
     double sst;     /* sum (y - y_mean)^2 over n_total, rils_rols_cpp.cpp:43 */
     int32_t sm_count;
     int32_t exact_max_n;
+    int32_t n_gpus; /* devices this engine object drives itself (rr_engine_create_sharded), else 1 */
+    int32_t world;  /* ranks the rows are sharded over (n_gpus, or the size of the installed communicator / hook) */
 } rr_engine_info;
 
 typedef struct rr_stats {
@@ -173,6 +176,9 @@ typedef struct rr_stats {
     double w_shared;           /* last batch: same count for the work actually issued (after CSE, all passes) */
     uint64_t h2d_bytes;        /* last batch */
     uint64_t d2h_bytes;        /* last batch */
+    double last_host_ms;       /* last batch: host wall time of rr_score_batch (analyse + planning + waits) */
+    double ingest_ms;          /* engine creation: upload + device-side transpose / gather + target statistics */
+    uint64_t collectives;      /* NCCL collectives issued by the engine itself (0 with the callback hook) */
 } rr_stats;
 
 /*
@@ -192,7 +198,26 @@ RR_API int rr_engine_create(const double *X_feature_major, const double *y, int6
  * (rils_rols_cpp.cpp:690-696): the transpose runs on the device. */
 RR_API int rr_engine_create_rowmajor(const double *X_row_major, const double *y, int64_t n, int32_t d,
                               int32_t device, uint32_t flags, rr_engine **out);
+/*
+ * ONE engine object over n_gpus devices of this process (devices 0 .. n_gpus-1; n_gpus <= 0 = all
+ * visible). Rows are sharded in contiguous blocks, every device sweeps its block with the same plan, and the
+ * per-candidate partial reductions are summed by NCCL (ncclCommInitAll, one ncclReduce per sweep on the engines'
+ * streams, no host synchronisation in between); the solves run on device 0. X is feature-major unless
+ * RR_FLAG_X_ROWMAJOR is set. row_index (may be NULL) selects and orders the rows: row i of the engine is row
+ * row_index[i] of X / y, n_rows of them - the shuffled sub-sample of rils_rols_cpp.cpp:774-795, gathered on the
+ * device(s) instead of on the host (n_rows = n and row_index = NULL: all rows in order). With n_gpus == 1 this is
+ * rr_engine_create plus the device-side gather. Always takes the Gram path.
+ */
+RR_API int rr_engine_create_sharded(const double *X, const double *y, int64_t n, int32_t d, const int32_t *row_index,
+                                    int64_t n_rows, int32_t n_gpus, uint32_t flags, rr_engine **out);
 RR_API void rr_engine_destroy(rr_engine *e);
+
+/* One process per GPU (torchrun): NCCL inside the engine instead of the callback below. Rank 0 obtains a unique id
+ * (128 bytes, ncclGetUniqueId), the caller broadcasts it by whatever means it has, and every rank installs it:
+ * the engine then all-reduces its partial reductions itself, on its own stream, with no host involvement.
+ * Collective: all ranks must call rr_engine_comm_init together. */
+RR_API int rr_comm_unique_id(void *id128);
+RR_API int rr_engine_comm_init(rr_engine *e, const void *id128, int32_t rank, int32_t world);
 
 /* Install the all-reduce hook (this engine holds shard `rank` of `world`) and recompute
  * y_mean / sst over all ranks. fn == NULL removes it. */
@@ -216,6 +241,22 @@ RR_API int rr_predict(rr_engine *e, const uint32_t *code, int32_t code_len, cons
 RR_API int rr_predict_rowmajor(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts,
                         int32_t n_consts, const double *X_row_major, int64_t n, int32_t d,
                         double *out);
+/* predict_proba() of the classifier through the same interpreter: out[2 i] = 1 - p_i, out[2 i + 1] = p_i with
+ * p = 1 / (1 + exp(-2 (yhat - 0.5))), the logistic of average_log_loss (rils_rols_cpp.cpp:69). (The reference's
+ * Python predict_proba applies utils.logistic to the already thresholded prediction, rils_rols.py:177-179; that
+ * wrapper keeps working on predict().) out has 2 n doubles. */
+RR_API int rr_predict_proba_rowmajor(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts,
+                                     int32_t n_consts, const double *X_row_major, int64_t n, int32_t d, double *out);
+
+/* relevant_features(), rils_rols_cpp.cpp:753-770: r2[j] = R2(X[j], y) with the reference's (truth, prediction) =
+ * (feature, target) argument order, i.e. 1 - sum (x_j - y)^2 / sum (x_j - mean x_j)^2, for every feature column of
+ * the engine (one device reduction; the host keeps the 200 best when d > 200). r2 has d doubles. */
+RR_API int rr_feature_r2(rr_engine *e, double *r2);
+
+/* Copies rows [row0, row0 + rows) of the engine's resident matrix back: Xout feature-major rows x d (column stride
+ * `rows`), yout rows values; either may be NULL. Test hook for the device-side ingest (same row order and bits as the
+ * reference's host loops). */
+RR_API int rr_engine_read_rows(rr_engine *e, int64_t row0, int64_t rows, double *Xout_feature_major, double *yout);
 
 /* Measured FP64-pipe peak (thread-instructions / s) of the engine's device from a
  * DFMA-only microkernel: the roofline denominator of SURVEY 8(d). */

@@ -27,6 +27,7 @@ FLAG_FORCE_GRAM = 1 << 0
 FLAG_FORCE_EXACT = 1 << 1
 FLAG_NO_CSE = 1 << 2
 FLAG_X_DEVICE = 1 << 3
+FLAG_X_ROWMAJOR = 1 << 4
 
 RES_NONFINITE = 1 << 0
 RES_RANKDEF = 1 << 1
@@ -123,7 +124,7 @@ class rr_batch(C.Structure):
         ("code", C.POINTER(C.c_uint32)),
         ("consts", C.POINTER(C.c_double)),
         ("n_consts", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_code", C.c_int32),
     ]
 
 
@@ -186,7 +187,7 @@ class Batch:
         s.code = _ptr(self.code, C.c_uint32)
         s.consts = _ptr(self.consts, C.c_double)
         s.n_consts = self._n_consts
-        s.reserved = 0
+        s.n_code = int(self.code.size)
         return s
 
     def subset(self, idx: Sequence[int]) -> "Batch":

@@ -387,9 +387,12 @@ void compile_postfix(const Expr &e, std::vector<uint32_t> &code, std::vector<dou
     if (e.arity() >= 1) compile_postfix(*e.left, code, consts);
     if (e.arity() >= 2) compile_postfix(*e.right, code, consts);
     if (e.is(Op::CONST)) {
+        // the argument field of a code word has 24 bits (include/rr_b200.h): a batch with more constants must be split
+        if (consts.size() >= (1u << 24)) throw std::length_error("more than 2^24 constants in one batch");
         code.push_back(RR_INS(RR_OP_CONST, consts.size()));
         consts.push_back(e.value);
     } else if (e.is(Op::VAR)) {
+        if (e.var < 0 || e.var >= (1 << 24)) throw std::length_error("feature index does not fit the 24-bit argument field");
         code.push_back(RR_INS(RR_OP_VAR, e.var));
     } else {
         code.push_back(RR_INS((uint32_t)e.type, 0));

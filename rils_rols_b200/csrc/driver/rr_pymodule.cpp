@@ -72,6 +72,15 @@ public:
         return out;
     }
 
+    py::array_t<double> predict_proba(DArr X, int data_cnt, int feat_cnt)
+    {
+        if (X.size() != (py::ssize_t)data_cnt * feat_cnt) throw py::value_error("Size of X does not match data_cnt * feat_cnt");
+        py::array_t<double> out({(py::ssize_t)data_cnt, (py::ssize_t)2});
+        s_.predict_proba(X.data(), data_cnt, feat_cnt, out.mutable_data());
+        return out;
+    }
+    void set_classifier_objective(bool on) { s_.set_classifier_objective(on); }
+
     std::string get_model_string() { return s_.model_string(); }
     double get_best_time() const { return s_.best_time(); }
     double get_total_time() const { return s_.total_time(); }
@@ -114,6 +123,8 @@ public:
         d["nonfinite"] = st.nonfinite;
         d["distinct_terms"] = st.distinct_terms;
         d["term_instances"] = st.term_instances;
+        d["ingest_ms"] = st.ingest_ms;
+        d["collectives"] = st.collectives;
         return d;
     }
     py::tuple get_model_program() const
@@ -202,6 +213,8 @@ PYBIND11_MODULE(rils_rols_cpp, m)
         .def("get_fit_calls", &PyRilsRols::get_fit_calls)
         .def("get_total_time", &PyRilsRols::get_total_time)
         // extras (not in the reference)
+        .def("predict_proba", &PyRilsRols::predict_proba)
+        .def("set_classifier_objective", &PyRilsRols::set_classifier_objective)
         .def("set_trace", &PyRilsRols::set_trace)
         .def("get_trace", &PyRilsRols::get_trace)
         .def("get_engine_stats", &PyRilsRols::get_engine_stats)

@@ -118,7 +118,7 @@ struct Search::BatchBuilder {
         b.code = code.data();
         b.consts = consts.data();
         b.n_consts = (int32_t)consts.size();
-        b.reserved = 0;
+        b.n_code = (int32_t)code.size();
         return b;
     }
 };
@@ -128,6 +128,8 @@ Search::Search(const SearchParams &p) : p_(p)
 {
     const char *t = std::getenv("RR_B200_TRACE");
     trace_ = t && *t && *t != '0';
+    const char *co = std::getenv("RR_B200_CLASSIFIER_OBJECTIVE");
+    classifier_objective_ = co && *co && *co != '0';
     reset();
 }
 
@@ -396,16 +398,45 @@ int Search::compare_fitness(const Fitness &a, const Fitness &b) const  // :547-5
     return 0;
 }
 
-Fitness Search::score_single(const Expr &tree)
+// RR_FLAG_CLASSIFIER_OBJECTIVE of the driver (default off): the objective the reference's authors
+// left commented out at :527 - loss = 1 - classification_accuracy - with average_log_loss (:63-76) in the second slot,
+// both from the engine's RI_CLSMET reduction of the scored model. NaN in either -> sentinel, like :529-530.
+Fitness Search::classifier_fitness_from(double accuracy, double log_loss, int size) const
+{
+    const double loss = 1 - accuracy;
+    if (loss != loss || log_loss != log_loss) return Fitness{1000, 1000, 1000};
+    return Fitness{loss, log_loss, size};
+}
+
+// fitness of fully specified trees (no OLS): one EVAL_ONLY batch; with the classifier objective the metrics call
+std::vector<Fitness> Search::score_trees(const std::vector<const Expr *> &trees, std::vector<double> *ssr_out)
 {
     BatchBuilder bb(RR_MODE_EVAL_ONLY);
-    bb.add_eval(tree);
+    for (const Expr *t : trees) bb.add_eval(*t);
     rr_batch b = bb.view();
-    double ssr = 0.0;
-    rr_result r{nullptr, nullptr, &ssr, nullptr};
+    const size_t m = trees.size();
+    std::vector<Fitness> f(m);
+    if (classifier_objective()) {
+        std::vector<double> acc(m), ll(m);
+        engine_check(rr_classifier_metrics(eng_, &b, acc.data(), ll.data(), nullptr), "rr_classifier_metrics");
+        for (size_t i = 0; i < m; ++i) f[i] = classifier_fitness_from(acc[i], ll[i], bb.eval_size[i]);
+        if (ssr_out) ssr_out->assign(m, 0.0);
+        return f;
+    }
+    std::vector<double> ssr(m);
+    rr_result r{nullptr, nullptr, ssr.data(), nullptr};
     engine_check(rr_score_batch(eng_, &b, &r), "rr_score_batch");
+    for (size_t i = 0; i < m; ++i) f[i] = fitness_from(ssr[i], bb.eval_size[i]);
+    if (ssr_out) *ssr_out = std::move(ssr);
+    return f;
+}
+
+Fitness Search::score_single(const Expr &tree)
+{
+    std::vector<const Expr *> one{&tree};
+    const Fitness f = score_trees(one, nullptr)[0];
     fit_calls_++;
-    return fitness_from(ssr, bb.eval_size[0]);
+    return f;
 }
 
 ExprP Search::tune_single(const Expr &tree, Fitness *fit)
@@ -418,6 +449,10 @@ ExprP Search::tune_single(const Expr &tree, Fitness *fit)
     rr_result r{coef.data(), nullptr, &ssr, nullptr};
     engine_check(rr_score_batch(eng_, &b, &r), "rr_score_batch");
     ExprP tuned = rebuild_from_coefficients(bb.factors[0], coef.data());
+    if (classifier_objective()) {
+        *fit = score_single(*tuned);  // counts the fit call
+        return tuned;
+    }
     fit_calls_++;
     *fit = fitness_from(ssr, size_of(*tuned));
     return tuned;
@@ -478,12 +513,24 @@ ExprP Search::local_search(const Expr &start)
             tb->curr_size = std::get<2>(curr_fit);
             tb->fit_calls_before = fit_calls_;
         }
+        std::vector<Fitness> cls_fit;
+        if (classifier_objective()) {
+            // the tuned trees themselves (coefficients from the least-squares fit as in the reference), scored with the
+            // classifier metrics in one batch
+            std::vector<ExprP> tuned(m);
+            std::vector<const Expr *> ptrs(m);
+            for (size_t j = 0; j < m; ++j) {
+                tuned[j] = rebuild_from_coefficients(bb.factors[j], coef.data() + bb.cand_term_begin[j] + j);
+                ptrs[j] = tuned[j].get();
+            }
+            cls_fit = score_trees(ptrs, nullptr);
+        }
         for (size_t j = 0; j < m; ++j) {  // :611-639 replay
             if (finished()) break;
             const double *cj = coef.data() + bb.cand_term_begin[j] + j;
             const int size = rebuilt_size(bb.factors[j], cj);
             fit_calls_++;  // the fitness() call of :616
-            Fitness f = fitness_from(ssr[j], size);
+            Fitness f = classifier_objective() ? cls_fit[j] : fitness_from(ssr[j], size);
             if (tb) {
                 tb->size[j] = size;
                 tb->consumed[j] = 1;
@@ -527,52 +574,43 @@ void Search::fit(const double *Xr, const double *y, int64_t n_all, int32_t d)
     std::vector<int> selected(n_all);
     std::iota(selected.begin(), selected.end(), 0);
     std::shuffle(selected.begin(), selected.end(), std::default_random_engine(p_.random_state));  // :778
-    std::vector<double> Xs((size_t)sample_cnt * d), ys(sample_cnt);
-    for (int64_t ix = 0; ix < sample_cnt; ++ix) {  // :788-795
-        const int i = selected[ix];
-        std::copy(Xr + (size_t)i * d, Xr + (size_t)(i + 1) * d, Xs.begin() + (size_t)ix * d);
-        ys[ix] = y[i];
-    }
-    // relevant_features, :753-770 (host pre-processing, only active beyond 200 features)
-    std::vector<int> rel;
-    const int max_feat = 200;
-    if (d <= max_feat) {
-        rel.resize(d);
-        std::iota(rel.begin(), rel.end(), 0);
-    } else {
-        std::vector<std::tuple<double, int>> by_r2;
-        for (int j = 0; j < d; ++j) {
-            // R2(X[j], y) with (truth, prediction) = (feature, target), :763
-            double mean = 0.0;
-            for (int64_t i = 0; i < sample_cnt; ++i) mean += Xs[(size_t)i * d + j];
-            mean /= (double)sample_cnt;
-            double ssr = 0.0, sst = 0.0;
-            for (int64_t i = 0; i < sample_cnt; ++i) {
-                const double x = Xs[(size_t)i * d + j];
-                ssr += (x - ys[i]) * (x - ys[i]);
-            }
-            for (int64_t i = 0; i < sample_cnt; ++i) {
-                const double x = Xs[(size_t)i * d + j];
-                sst += (x - mean) * (x - mean);
-            }
-            by_r2.emplace_back(1 - ssr / sst, j);
-        }
-        std::sort(by_r2.begin(), by_r2.end(), std::greater<>());
-        for (int i = 0; i < max_feat; ++i) rel.push_back(std::get<1>(by_r2[i]));
-    }
-    setup_nodes(rel);
-
+    // :788-795 without the host loops: the engine gathers rows selected[0 .. sample_cnt) straight from the caller's
+    // row-major matrix on the device(s) (same row order, same bits). Large data sets are sharded by sample over all
+    // visible GPUs inside the engine (RR_B200_GPUS overrides: a count, 0 = all).
     if (eng_) {
         rr_engine_destroy(eng_);
         eng_ = nullptr;
     }
-    const int rc = rr_engine_create_rowmajor(Xs.data(), ys.data(), sample_cnt, d, -1, RR_FLAG_DEFAULT, &eng_);
+    int n_gpus = 1;
+    {
+        const char *g = std::getenv("RR_B200_GPUS");
+        if (g && *g) n_gpus = std::atoi(g);
+        else if (sample_cnt >= ((int64_t)1 << 22)) n_gpus = 0;
+    }
+    static_assert(sizeof(int) == sizeof(int32_t), "row index type");
+    const int rc = rr_engine_create_sharded(Xr, y, n_all, d, reinterpret_cast<const int32_t *>(selected.data()), sample_cnt, n_gpus,
+                                            RR_FLAG_X_ROWMAJOR, &eng_);
     if (rc != RR_OK) throw std::runtime_error(std::string("rr_engine_create failed: ") + rr_last_error(nullptr));
     rr_engine_info info;
     engine_check(rr_engine_get_info(eng_, &info), "rr_engine_get_info");
     n_ = sample_cnt;
     d_ = d;
     sst_ = info.sst;
+    // relevant_features, :753-770 (only active beyond 200 features): R2(X[j], y) per feature is one device reduction
+    std::vector<int> rel;
+    const int max_feat = 200;
+    if (d <= max_feat) {
+        rel.resize(d);
+        std::iota(rel.begin(), rel.end(), 0);
+    } else {
+        std::vector<double> r2(d);
+        engine_check(rr_feature_r2(eng_, r2.data()), "rr_feature_r2");
+        std::vector<std::tuple<double, int>> by_r2;
+        for (int j = 0; j < d; ++j) by_r2.emplace_back(r2[j], j);
+        std::sort(by_r2.begin(), by_r2.end(), std::greater<>());
+        for (int i = 0; i < max_feat; ++i) rel.push_back(std::get<1>(by_r2[i]));
+    }
+    setup_nodes(rel);
 
     final_ = std::make_unique<Expr>(0.0);  // :799-800
     final_fit_ = score_single(*final_);
@@ -606,13 +644,12 @@ void Search::fit(const double *Xr, const double *y, int64_t n_all, int32_t d)
         if (!picked.empty()) {
             BatchBuilder bb(RR_MODE_EVAL_ONLY);
             for (size_t i : picked) bb.add_eval(perts[i]);
-            rr_batch b = bb.view();
-            std::vector<double> ssr(picked.size());
-            rr_result r{nullptr, nullptr, ssr.data(), nullptr};
-            engine_check(rr_score_batch(eng_, &b, &r), "rr_score_batch");
+            std::vector<const Expr *> ptrs;
+            for (size_t i : picked) ptrs.push_back(&perts[i]);
+            std::vector<double> ssr;
+            const std::vector<Fitness> pf = score_trees(ptrs, &ssr);
             fit_calls_ += (int)picked.size();
-            for (size_t k = 0; k < picked.size(); ++k)
-                by_r2.emplace_back(std::get<0>(fitness_from(ssr[k], bb.eval_size[k])), picked[k]);
+            for (size_t k = 0; k < picked.size(); ++k) by_r2.emplace_back(std::get<0>(pf[k]), picked[k]);
             if (trace_) {
                 trace_log_.emplace_back();
                 TraceBatch &tb = trace_log_.back();
@@ -661,6 +698,18 @@ void Search::predict(const double *Xr, int64_t n, int32_t d, double *out) const 
                  "rr_predict");
     if (p_.classification)
         for (int64_t i = 0; i < n; ++i) out[i] = out[i] >= 0.5 ? 1.0 : 0.0;
+}
+
+void Search::predict_proba(const double *Xr, int64_t n, int32_t d, double *out) const
+{
+    if (!final_ || !eng_) throw std::runtime_error("predict_proba before fit");
+    std::vector<uint32_t> code;
+    std::vector<double> consts;
+    compile_postfix(*final_, code, consts);
+    const double dummy = 0.0;
+    engine_check(rr_predict_proba_rowmajor(eng_, code.data(), (int32_t)code.size(), consts.empty() ? &dummy : consts.data(),
+                                           (int32_t)consts.size(), Xr, n, d, out),
+                 "rr_predict_proba");
 }
 
 std::string Search::model_string() const

@@ -61,6 +61,7 @@ public:
     // X row-major n x d (the numpy layout of the pybind boundary), y n values
     void fit(const double *X_rowmajor, const double *y, int64_t n, int32_t d);
     void predict(const double *X_rowmajor, int64_t n, int32_t d, double *out) const;
+    void predict_proba(const double *X_rowmajor, int64_t n, int32_t d, double *out) const;  // n x 2: (1 - p, p)
     std::string model_string() const;
     double best_time() const { return best_time_; }
     double total_time() const { return total_time_; }
@@ -71,6 +72,9 @@ public:
     void setup_nodes_for(int32_t d);  // allowed node set for d features without data
     std::vector<Expr> all_candidates(const Expr &solution, bool local_search) const;
     void set_trace(bool on) { trace_ = on; }
+    // classification only: score with (1 - accuracy, log-loss, size) instead of (1 - R2, RMSE, size); default off = reference
+    void set_classifier_objective(bool on) { classifier_objective_ = on; }
+    bool classifier_objective() const { return p_.classification && classifier_objective_; }
     const std::vector<TraceBatch> &trace() const { return trace_log_; }
     rr_stats engine_stats() const { return stats_; }
 
@@ -91,6 +95,7 @@ private:
     double best_time_ = 0.0, total_time_ = 0.0;
     std::vector<Expr> allowed_;
     bool trace_ = false;
+    bool classifier_objective_ = false;
     std::vector<TraceBatch> trace_log_;
 
     void reset();
@@ -101,6 +106,8 @@ private:
     std::vector<Expr> perturb_candidates(const Expr &old_node) const;
 
     Fitness fitness_from(double ssr, int size) const;
+    Fitness classifier_fitness_from(double accuracy, double log_loss, int size) const;
+    std::vector<Fitness> score_trees(const std::vector<const Expr *> &trees, std::vector<double> *ssr_out);
     double fitness_value(const Fitness &f) const;
     int compare_fitness(const Fitness &a, const Fitness &b) const;
     Fitness score_single(const Expr &tree);                       // fitness(), one EVAL_ONLY candidate

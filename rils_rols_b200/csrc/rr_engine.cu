@@ -8,6 +8,8 @@
 // buffers owned by the engine. There is no CPU fallback: without a CUDA device of compute
 // capability 10.x every entry point fails with RR_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and enumerators only: the library is loaded at run time (see NcclApi)
 
 #include <algorithm>
 #include <chrono>
@@ -17,6 +19,8 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -84,6 +88,57 @@ struct HostBuf {  // pinned
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// NCCL is bound at run time: a process that never shards rows needs no NCCL at all, and under torchrun the copy
+// torch has already loaded (same SONAME) is the one that is picked up - two NCCL copies in one process do not mix.
+struct NcclApi {
+    void *h = nullptr;
+    std::string err;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+
+    template <typename F> bool sym(F &f, const char *name)
+    {
+        f = reinterpret_cast<F>(dlsym(h, name));
+        if (!f) err = std::string("NCCL symbol missing: ") + name;
+        return f != nullptr;
+    }
+    bool load()
+    {
+        if (h) return true;
+        const char *env = std::getenv("RR_B200_NCCL_LIB");
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy this process already has (torch's)
+        if (!h && env && *env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) {
+            const char *de = dlerror();
+            err = std::string("cannot load libnccl.so.2: ") + (de ? de : "?");
+            return false;
+        }
+        const bool ok = sym(GetUniqueId, "ncclGetUniqueId") && sym(CommInitRank, "ncclCommInitRank") &&
+                        sym(CommInitAll, "ncclCommInitAll") && sym(CommDestroy, "ncclCommDestroy") &&
+                        sym(AllReduce, "ncclAllReduce") && sym(Reduce, "ncclReduce") && sym(AllGather, "ncclAllGather") &&
+                        sym(GroupStart, "ncclGroupStart") && sym(GroupEnd, "ncclGroupEnd") &&
+                        sym(GetErrorString, "ncclGetErrorString");
+        if (!ok) h = nullptr;
+        return ok;
+    }
+};
+NcclApi &nccl()
+{
+    static NcclApi api;
+    return api;
+}
+std::mutex g_nccl_mu;
+
 double env_double(const char *name, double dflt)
 {
     const char *s = std::getenv(name);
@@ -102,24 +157,78 @@ constexpr size_t kSmemPerBlockMax = 232448;
 constexpr size_t kSmemPerSM = 233472;
 constexpr size_t kSmemReserved = 1024;
 
-__global__ void k_transpose_rowmajor(const double *__restrict__ Xr, int64_t n, int32_t d, double *__restrict__ Xc,
-                                     int64_t ld)
+// Rows [0, rows) of a row-major chunk Xr (rows x d) -> feature-major engine matrix: row r goes to position
+// pos[r] (pos == nullptr: dst0 + r; pos[r] < 0: not selected). 32 x 32 tiles through shared memory: the reads are
+// coalesced; with an index the writes are scattered 8-byte stores (the shuffle of rils_rols_cpp.cpp:777-795).
+__global__ void k_ingest_rows(const double *__restrict__ Xr, const double *__restrict__ yr, int64_t rows, int32_t d,
+                              const int32_t *__restrict__ pos, int64_t dst0, int64_t dst_lo, int64_t dst_hi,
+                              double *__restrict__ Xc, int64_t ld, double *__restrict__ yc)
 {
-    // 32 x 32 tiles through shared memory: coalesced on both sides
     __shared__ double tile[32][33];
     const int64_t i0 = (int64_t)blockIdx.x * 32;
     const int j0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int64_t i = i0 + r;
         const int j = j0 + threadIdx.x;
-        tile[r][threadIdx.x] = (i < n && j < d) ? Xr[i * d + j] : 0.0;
+        tile[r][threadIdx.x] = (i < rows && j < d) ? Xr[i * d + j] : 0.0;
     }
     __syncthreads();
+    const int64_t i = i0 + threadIdx.x;
+    int64_t dst = -1;
+    if (i < rows) {
+        dst = pos ? (int64_t)pos[i] : dst0 + i;
+        if (dst < dst_lo || dst >= dst_hi) dst = -1;
+    }
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int j = j0 + r;
-        const int64_t i = i0 + threadIdx.x;
-        if (j < d && i < n) Xc[(int64_t)j * ld + i] = tile[threadIdx.x][r];
+        if (j < d && dst >= 0) Xc[(int64_t)j * ld + (dst - dst_lo)] = tile[threadIdx.x][r];
     }
+    if (blockIdx.y == 0 && threadIdx.y == 0 && dst >= 0 && yr) yc[dst - dst_lo] = yr[i];
+}
+
+// relevant_features (rils_rols_cpp.cpp:753-770), per feature column: pass 0 -> sum x; pass 1 -> sum (x - mean)^2 and
+// sum (x - y)^2. Deterministic: fixed grid, block partials summed on the host in order.
+__global__ void k_feature_stats(const double *__restrict__ X, int64_t ld, const double *__restrict__ y, int64_t n,
+                                const double *__restrict__ mean, int pass, double *__restrict__ partial)
+{
+    __shared__ double s0[256], s1[256];
+    const int j = blockIdx.y;
+    const double *x = X + (size_t)j * ld;
+    const double m = pass ? mean[j] : 0.0;
+    double a = 0.0, b = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        if (pass == 0) {
+            a += v;
+        } else {
+            a = fma(v - m, v - m, a);
+            b = fma(v - y[i], v - y[i], b);
+        }
+    }
+    s0[threadIdx.x] = a;
+    s1[threadIdx.x] = b;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+            s0[threadIdx.x] += s0[threadIdx.x + st];
+            s1[threadIdx.x] += s1[threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[2 * ((size_t)j * gridDim.x + blockIdx.x)] = s0[0];
+        partial[2 * ((size_t)j * gridDim.x + blockIdx.x) + 1] = s1[0];
+    }
+}
+
+// predict_proba epilogue: (1 - p, p) with p = 1 / (1 + exp(-2 (yhat - 0.5))), rils_rols_cpp.cpp:69
+__global__ void k_proba(const double *__restrict__ yhat, int64_t n, double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double p = 1.0 / (1.0 + exp(-2.0 * (yhat[i] - 0.5)));
+    out[2 * i] = 1.0 - p;
+    out[2 * i + 1] = p;
 }
 
 // deterministic two-stage sum of f(y): mode 0 -> sum y ; mode 1 -> writes yc = y - mean and sums yc, yc^2
@@ -196,6 +305,14 @@ struct rr_engine {
     rr_allreduce_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
     int rank = 0, world = 1;
+    // sample sharding, NCCL inside the engine. Single process: this object is shard 0 (the leader) and owns
+    // `peers`, one engine per further device, each with a communicator of one ncclCommInitAll clique.
+    // One process per GPU: `comm` is this rank's communicator (rr_engine_comm_init).
+    std::vector<rr_engine *> peers;
+    ncclComm_t comm = nullptr;
+    bool comm_ranks = false;  // comm spans processes (world / rank above); false with peers: comm spans this object's shards
+    int64_t n_object = 0;     // rows held by this object over all its shards
+    DevBuf d_px, d_pr, d_pout;  // predict(): feature-major chunk, row-major chunk, output chunk
     // grow-only work buffers
     DevBuf d_ins2, d_chunks2, d_cols2, d_acc2;  // second sweep in flight (run_gram plans the batch in two halves)
     DevBuf d_ins, d_chunks, d_cols, d_acc, d_dots, d_rdots, d_tab, d_rtab, d_ws, d_wsoff, d_list, d_coef, d_cs,
@@ -216,8 +333,26 @@ struct rr_engine {
         error = std::string(what) + ": " + cudaGetErrorString(e);
         return RR_ERR_CUDA;
     }
+    int nccl_fail(ncclResult_t r, const char *what)
+    {
+        error = std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error");
+        return RR_ERR_COLLECTIVE;
+    }
+    bool grouped() const { return !peers.empty(); }  // rows spread over devices of this object
+    bool sharded() const { return peers.empty() && world > 1 && (allreduce || comm); }  // ... over other processes
+    bool rows_split() const { return grouped() || sharded(); }
     void free_all()
     {
+        for (rr_engine *p : peers) {
+            cudaSetDevice(p->device);
+            p->free_all();
+            delete p;
+        }
+        peers.clear();
+        cudaSetDevice(device);
+        if (comm && nccl().CommDestroy) nccl().CommDestroy(comm);
+        comm = nullptr;
+        for (DevBuf *b : {&d_px, &d_pr, &d_pout}) b->release();
         for (DevBuf *b : {&X, &d_ins2, &d_chunks2, &d_cols2, &d_acc2, &d_ins, &d_chunks, &d_cols, &d_acc, &d_dots, &d_rdots, &d_tab, &d_rtab, &d_ws, &d_wsoff,
                           &d_list, &d_coef, &d_cs, &d_nzp, &d_ssr, &d_flags, &d_status, &d_delta, &d_V, &d_A, &d_rhs,
                           &d_aux, &d_perm, &d_ctb, &d_tid, &d_misc, &d_gather, &d_t0, &d_t1, &d_t2, &d_t3, &d_t4})
@@ -234,6 +369,11 @@ struct rr_engine {
     do {                                                      \
         cudaError_t _e = (call);                              \
         if (_e != cudaSuccess) return e->cuda_fail(_e, #call); \
+    } while (0)
+#define NC(call)                                               \
+    do {                                                       \
+        ncclResult_t _r = (call);                              \
+        if (_r != ncclSuccess) return e->nccl_fail(_r, #call); \
     } while (0)
 
 namespace {
@@ -339,22 +479,32 @@ int sweep_gx(rr_engine *e, const SweepCfg &c, bool special, size_t smem, int n_c
     return std::min(gx, n_tiles);
 }
 
-// Runs one plan: zero accumulators, launch the interpreter, reduce rows into `dots` (device),
-// all-reduce across ranks when sharded. dd: the plan holds DOTDD reductions only.
-// set / dots_off / sync: run_gram plans a large batch in two halves and launches the first while it plans the
-// second, so two sweeps can be in flight: `set` picks the device buffers and the event pair, the reduced dots
-// land at dots + dots_off (the caller has sized `dots` for both: growing it here would drop the first half),
-// and with sync = false the call returns right after the launches (finish_sweep reads the time later).
-int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf &dots, bool dd, double *stg, int64_t ld_stg,
-              int set = 0, size_t dots_off = 0, bool sync = true)
+// which of an engine's reduced-dot buffers a sweep writes (the same member on every shard)
+using DotsMember = DevBuf rr_engine::*;
+// the matrix a launch sweeps: the engine's resident one, or a chunk of predict()'s input
+struct XView {
+    const double *X;
+    int64_t ld, n;
+};
+std::vector<rr_engine *> shards_of(rr_engine *e)
 {
-    DevBuf &d_ins = set ? e->d_ins2 : e->d_ins, &d_chunks = set ? e->d_chunks2 : e->d_chunks;
-    DevBuf &d_cols = set ? e->d_cols2 : e->d_cols, &d_acc = set ? e->d_acc2 : e->d_acc;
-    cudaEvent_t ev0 = e->ev[set ? 4 : 2], ev1 = e->ev[set ? 5 : 3];
-    if (P.chunks.empty()) return RR_OK;
+    std::vector<rr_engine *> v{e};
+    v.insert(v.end(), e->peers.begin(), e->peers.end());
+    return v;
+}
+
+// One shard, one plan: upload the plan, zero the accumulators, launch the interpreter on s->stream, reduce the block
+// rows into (s->*dots) + dots_off. No synchronisation. `e` (the leader) only receives the error text.
+int launch_shard(rr_engine *e, rr_engine *s, const rr::SweepPlan &P, const std::vector<RRIns> &ins_padded, const SweepCfg &cfg,
+                 const XView &view, DotsMember dots, bool dd, double *stg, int64_t ld_stg, int set, size_t dots_off)
+{
+    DevBuf &d_ins = set ? s->d_ins2 : s->d_ins, &d_chunks = set ? s->d_chunks2 : s->d_chunks;
+    DevBuf &d_cols = set ? s->d_cols2 : s->d_cols, &d_acc = set ? s->d_acc2 : s->d_acc;
+    cudaEvent_t ev0 = s->ev[set ? 4 : 2], ev1 = s->ev[set ? 5 : 3];
+    CU(cudaSetDevice(s->device));
     const int T = cfg.T();
     const int NW = cfg.TH / 32;
-    const int n_tiles = (int)((e->n + T - 1) / T);
+    const int n_tiles = (int)((view.n + T - 1) / T);
     const size_t smem = (size_t)std::max(P.max_tile_cols, 1) * T * 8 + rr::sweep_ring_smem(NW, cfg.slack);
     if (smem > cfg.dyn_smem_budget() + rr::sweep_ring_smem(NW, cfg.slack)) return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
     bool special = dd;
@@ -363,34 +513,34 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     SweepKernel kern = sweep_kernel_for(cfg, special);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemPerBlockMax - rr::sweep_static_smem())));
     const int n_chunks = (int)P.chunks.size();
-    int gx = sweep_gx(e, cfg, special, smem, n_chunks, std::max(1, n_tiles));
+    int gx = sweep_gx(s, cfg, special, smem, n_chunks, std::max(1, n_tiles));
     const int64_t stride = round_up(std::max(P.n_dots, 1), 32) + 32;
     // keep the accumulator rows within a sane budget
     const size_t row_budget = (size_t)env_double("RR_B200_ACC_BYTES", 6e9);
     const int rpb = dd ? NW : 1;  // accumulator rows per block: double-double plans keep one per warp
     while (gx > 1 && (size_t)gx * rpb * stride * 8 > row_budget) gx = (gx + 1) / 2;
     const int rows = gx * rpb;
-
-    // the kernel streams whole windows of kInsWindow instructions: pad the tail with ENDs
-    std::vector<RRIns> ins(P.ins);
-    RRIns endi;
-    std::memset(&endi, 0, sizeof(endi));
-    ins.resize(P.ins.size() + rr::kInsWindow, endi);
-    int rc;
-    if ((rc = upload(e, d_ins, ins.data(), ins.size()))) return rc;
-    if ((rc = upload(e, d_chunks, P.chunks.data(), P.chunks.size()))) return rc;
-    if ((rc = upload(e, d_cols, P.cols.data(), P.cols.size()))) return rc;
+    {
+        int rc;
+        if ((rc = upload(s, d_ins, ins_padded.data(), ins_padded.size())) || (rc = upload(s, d_chunks, P.chunks.data(), P.chunks.size())) ||
+            (rc = upload(s, d_cols, P.cols.data(), P.cols.size()))) {
+            if (s != e) e->error = s->error;
+            return rc;
+        }
+        if (s != e) e->stats.h2d_bytes += (ins_padded.size() * sizeof(RRIns) + P.chunks.size() * sizeof(RRChunk) + P.cols.size() * 4);
+    }
+    DevBuf &dbuf = s->*dots;
     if (P.n_dots > 0) {
         CU(d_acc.ensure((size_t)rows * stride * 8));
-        CU(cudaMemsetAsync(d_acc.p, 0, (size_t)rows * stride * 8, e->stream));
-        CU(dots.ensure((dots_off + (size_t)stride) * 8));
+        CU(cudaMemsetAsync(d_acc.p, 0, (size_t)rows * stride * 8, s->stream));
+        CU(dbuf.ensure((dots_off + (size_t)stride) * 8));
     } else {
         CU(d_acc.ensure(64));
     }
     rr::SweepArgs a;
-    a.X = e->X.as<double>();
-    a.ld = e->ld;
-    a.n = e->n;
+    a.X = view.X;
+    a.ld = view.ld;
+    a.n = view.n;
     a.ins = d_ins.as<RRIns>();
     a.chunks = d_chunks.as<RRChunk>();
     a.cols = d_cols.as<int32_t>();
@@ -401,50 +551,118 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DevBuf 
     a.ld_stg = ld_stg;
     a.n_tiles = n_tiles;
     a.dd_ring = env_int("RR_B200_DD_RING", 1);
-    CU(cudaEventRecord(ev0, e->stream));
-    kern<<<dim3(gx, n_chunks), cfg.TH, smem, e->stream>>>(a);
+    CU(cudaEventRecord(ev0, s->stream));
+    kern<<<dim3(gx, n_chunks), cfg.TH, smem, s->stream>>>(a);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(ev1, e->stream));
+    CU(cudaEventRecord(ev1, s->stream));
     e->stats.sweep_launches++;
     e->stats.kernel_launches++;
     if (P.n_dots > 0) {
         if (!dd) {
-            rr::rr_reduce_rows<<<(P.n_dots + 255) / 256, 256, 0, e->stream>>>(d_acc.as<double>(), stride, rows,
-                                                                            P.n_dots, dots.as<double>() + dots_off);
+            rr::rr_reduce_rows<<<(P.n_dots + 255) / 256, 256, 0, s->stream>>>(d_acc.as<double>(), stride, rows, P.n_dots,
+                                                                            dbuf.as<double>() + dots_off);
         } else {
-            rr::rr_reduce_rows_dd<<<(P.n_dots / 2 + 255) / 256, 256, 0, e->stream>>>(
-                d_acc.as<double>(), stride, rows, P.n_dots / 2, dots.as<double>() + dots_off);
+            rr::rr_reduce_rows_dd<<<(P.n_dots / 2 + 255) / 256, 256, 0, s->stream>>>(d_acc.as<double>(), stride, rows, P.n_dots / 2,
+                                                                                   dbuf.as<double>() + dots_off);
         }
         CU(cudaGetLastError());
         e->stats.kernel_launches++;
-        if (e->allreduce && e->world > 1) {
-            if (!dd) {
-                if (e->allreduce(dots.as<double>() + dots_off, (size_t)P.n_dots, e->stream, e->allreduce_user))
-                    return e->fail(RR_ERR_COLLECTIVE, "all-reduce hook failed");
-            } else {
-                // double-double pairs must not be summed in fp64: gather every rank's pairs with a
-                // sum-of-disjoint-segments all-reduce (exact), then add them in double-double here
-                const size_t len = (size_t)P.n_dots;
-                CU(e->d_gather.ensure(len * e->world * 8));
-                CU(cudaMemsetAsync(e->d_gather.p, 0, len * e->world * 8, e->stream));
-                CU(cudaMemcpyAsync(e->d_gather.as<double>() + len * e->rank, dots.as<double>() + dots_off, len * 8, cudaMemcpyDeviceToDevice,
-                                   e->stream));
-                if (e->allreduce(e->d_gather.p, len * e->world, e->stream, e->allreduce_user))
-                    return e->fail(RR_ERR_COLLECTIVE, "all-reduce hook failed");
-                rr::rr_reduce_rows_dd<<<(P.n_dots / 2 + 255) / 256, 256, 0, e->stream>>>(
-                    e->d_gather.as<double>(), (int64_t)len, e->world, P.n_dots / 2, dots.as<double>() + dots_off);
-                CU(cudaGetLastError());
-                e->stats.kernel_launches++;
-            }
-        }
     }
+    return RR_OK;
+}
+
+// Sum `count` doubles at (shard->*dots) + off over all shards / ranks, stream-ordered, no host synchronisation:
+// single-process engines reduce to the leader (only it solves), communicator and hook engines all-reduce.
+// dd: the buffer holds (hi, lo) pairs that must not be summed in fp64: every rank's pairs are gathered and
+// added in double-double by the caller's rr_reduce_rows_dd.
+int reduce_over_ranks(rr_engine *e, DotsMember dots, size_t off, size_t count, bool dd)
+{
+    if (!count) return RR_OK;
+    NcclApi &N = nccl();
+    if (e->grouped()) {
+        std::vector<rr_engine *> sh = shards_of(e);
+        const size_t G = sh.size();
+        if (dd)
+            for (rr_engine *s : sh) {
+                CU(cudaSetDevice(s->device));
+                CU(s->d_gather.ensure(count * G * 8));
+            }
+        NC(N.GroupStart());
+        for (rr_engine *s : sh) {
+            double *buf = (s->*dots).as<double>() + off;
+            if (!dd) NC(N.Reduce(buf, buf, count, ncclDouble, ncclSum, 0, s->comm, s->stream));
+            else NC(N.AllGather(buf, s->d_gather.p, count, ncclDouble, s->comm, s->stream));
+        }
+        NC(N.GroupEnd());
+        e->stats.collectives++;
+        CU(cudaSetDevice(e->device));
+        if (dd) {
+            rr::rr_reduce_rows_dd<<<(int)((count / 2 + 255) / 256), 256, 0, e->stream>>>(e->d_gather.as<double>(), (int64_t)count, (int)G,
+                                                                                       (int)(count / 2), (e->*dots).as<double>() + off);
+            CU(cudaGetLastError());
+            e->stats.kernel_launches++;
+        }
+        return RR_OK;
+    }
+    if (!e->sharded()) return RR_OK;
+    double *buf = (e->*dots).as<double>() + off;
+    if (!dd) {
+        if (e->comm) {
+            NC(N.AllReduce(buf, buf, count, ncclDouble, ncclSum, e->comm, e->stream));
+            e->stats.collectives++;
+        } else if (e->allreduce(buf, count, e->stream, e->allreduce_user)) {
+            return e->fail(RR_ERR_COLLECTIVE, "all-reduce hook failed");
+        }
+        return RR_OK;
+    }
+    CU(e->d_gather.ensure(count * e->world * 8));
+    if (e->comm) {
+        NC(N.AllGather(buf, e->d_gather.p, count, ncclDouble, e->comm, e->stream));
+        e->stats.collectives++;
+    } else {
+        // sum-of-disjoint-segments all-reduce (exact)
+        CU(cudaMemsetAsync(e->d_gather.p, 0, count * e->world * 8, e->stream));
+        CU(cudaMemcpyAsync(e->d_gather.as<double>() + count * e->rank, buf, count * 8, cudaMemcpyDeviceToDevice, e->stream));
+        if (e->allreduce(e->d_gather.p, count * e->world, e->stream, e->allreduce_user))
+            return e->fail(RR_ERR_COLLECTIVE, "all-reduce hook failed");
+    }
+    rr::rr_reduce_rows_dd<<<(int)((count / 2 + 255) / 256), 256, 0, e->stream>>>(e->d_gather.as<double>(), (int64_t)count, e->world,
+                                                                               (int)(count / 2), buf);
+    CU(cudaGetLastError());
+    e->stats.kernel_launches++;
+    return RR_OK;
+}
+
+// Runs one plan over every shard of the engine: launch the interpreter, reduce rows into the shard's `dots`, sum over
+// shards / ranks. dd: the plan holds DOTDD reductions only.
+// set / dots_off / sync: run_gram plans a large batch in pieces and launches a piece while it plans the next, so two
+// sweeps can be in flight: `set` picks the device buffers and the event pair, the reduced dots land at
+// dots + dots_off (the caller has sized `dots` for all pieces: growing it here would drop the earlier ones),
+// and with sync = false the call returns right after the launches (finish_sweep reads the time later).
+int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DotsMember dots, bool dd, double *stg, int64_t ld_stg,
+              int set = 0, size_t dots_off = 0, bool sync = true)
+{
+    if (P.chunks.empty()) return RR_OK;
+    // the kernel streams whole windows of kInsWindow instructions: pad the tail with ENDs
+    std::vector<RRIns> ins(P.ins);
+    RRIns endi;
+    std::memset(&endi, 0, sizeof(endi));
+    ins.resize(P.ins.size() + rr::kInsWindow, endi);
+    int rc = RR_OK;
+    for (rr_engine *s : shards_of(e)) {
+        const XView view{s->X.as<double>(), s->ld, s->n};
+        if ((rc = launch_shard(e, s, P, ins, cfg, view, dots, dd, stg, ld_stg, set, dots_off))) break;
+    }
+    if (e->grouped()) cudaSetDevice(e->device);
+    if (rc) return rc;
+    if (P.n_dots > 0 && (rc = reduce_over_ranks(e, dots, dots_off, (size_t)P.n_dots, dd))) return rc;
     e->stats.distinct_dots += P.n_dot_ins;
     e->stats.w_shared += P.w_issued;
     if (!sync) return RR_OK;
     // sweep time is read after the synchronisation
     CU(cudaStreamSynchronize(e->stream));
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventElapsedTime(&ms, e->ev[set ? 4 : 2], e->ev[set ? 5 : 3]);
     e->sweep_ms_accum += ms;
     return RR_OK;
 }
@@ -472,42 +690,66 @@ rr::PlanLimits limits_for(rr_engine *e, const SweepCfg &cfg, int n_cand)
     return lim;
 }
 
+// deterministic partial sums over one shard's rows: mode 0 -> {sum y, 0}; mode 1 -> writes yc = y - mean, {sum yc, sum yc^2}
+int y_partial(rr_engine *e, rr_engine *s, int mode, double mean, double out[2])
+{
+    const int blocks = 296;
+    CU(cudaSetDevice(s->device));
+    CU(s->d_misc.ensure(blocks * 2 * 8 + 64));
+    std::vector<double> part(blocks * 2);
+    double *y = s->X.as<double>() + (size_t)s->d * s->ld;
+    double *yc = s->X.as<double>() + (size_t)(s->d + 1) * s->ld;
+    k_y_stats<<<blocks, 256, 0, s->stream>>>(y, yc, s->n, mean, mode, s->d_misc.as<double>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(part.data(), s->d_misc.p, blocks * 2 * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    out[0] = out[1] = 0.0;
+    for (int i = 0; i < blocks; ++i) { out[0] += part[2 * i]; out[1] += part[2 * i + 1]; }
+    return RR_OK;
+}
+
+// a few doubles summed over the ranks of a communicator / hook (engine creation only)
+int allreduce_small(rr_engine *e, double *vals, int count)
+{
+    if (!e->sharded()) return RR_OK;
+    CU(cudaSetDevice(e->device));
+    CU(e->d_misc.ensure(64 + (size_t)count * 8));
+    CU(cudaMemcpyAsync(e->d_misc.p, vals, (size_t)count * 8, cudaMemcpyHostToDevice, e->stream));
+    if (e->comm) {
+        NC(nccl().AllReduce(e->d_misc.p, e->d_misc.p, (size_t)count, ncclDouble, ncclSum, e->comm, e->stream));
+    } else if (e->allreduce(e->d_misc.p, (size_t)count, e->stream, e->allreduce_user)) {
+        return e->fail(RR_ERR_COLLECTIVE, "all-reduce hook failed");
+    }
+    CU(cudaMemcpyAsync(vals, e->d_misc.p, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return RR_OK;
+}
+
 int compute_y_stats(rr_engine *e)
 {
-    // mean and centred sums, deterministic; all-reduced when sharded
-    const int blocks = 296;
-    CU(e->d_misc.ensure(blocks * 2 * 8 + 64));
-    std::vector<double> part(blocks * 2);
-    double *y = e->X.as<double>() + (size_t)e->d * e->ld;
-    double *yc = e->X.as<double>() + (size_t)(e->d + 1) * e->ld;
-    k_y_stats<<<blocks, 256, 0, e->stream>>>(y, yc, e->n, 0.0, 0, e->d_misc.as<double>());
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(part.data(), e->d_misc.p, blocks * 2 * 8, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    double sum_y = 0.0;
-    for (int i = 0; i < blocks; ++i) sum_y += part[2 * i];
-    double tot[2] = {sum_y, (double)e->n};
-    if (e->allreduce && e->world > 1) {
-        CU(cudaMemcpyAsync(e->d_misc.p, tot, 16, cudaMemcpyHostToDevice, e->stream));
-        if (e->allreduce(e->d_misc.p, 2, e->stream, e->allreduce_user)) return e->fail(RR_ERR_COLLECTIVE, "all-reduce hook failed");
-        CU(cudaMemcpyAsync(tot, e->d_misc.p, 16, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
+    // mean and centred sums, deterministic: block partials in fixed order, shards in order on the host,
+    // ranks by the collective
+    std::vector<rr_engine *> sh = shards_of(e);
+    double tot[2] = {0.0, 0.0};
+    int rc;
+    for (rr_engine *s : sh) {
+        double p[2];
+        if ((rc = y_partial(e, s, 0, 0.0, p))) return rc;
+        tot[0] += p[0];
+        tot[1] += (double)s->n;
     }
+    if ((rc = allreduce_small(e, tot, 2))) return rc;
     e->n_total = (int64_t)llround(tot[1]);
     e->y_mean = tot[0] / tot[1];
-    k_y_stats<<<blocks, 256, 0, e->stream>>>(y, yc, e->n, e->y_mean, 1, e->d_misc.as<double>());
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(part.data(), e->d_misc.p, blocks * 2 * 8, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < blocks; ++i) { s1 += part[2 * i]; s2 += part[2 * i + 1]; }
-    double tot2[2] = {s1, s2};
-    if (e->allreduce && e->world > 1) {
-        CU(cudaMemcpyAsync(e->d_misc.p, tot2, 16, cudaMemcpyHostToDevice, e->stream));
-        if (e->allreduce(e->d_misc.p, 2, e->stream, e->allreduce_user)) return e->fail(RR_ERR_COLLECTIVE, "all-reduce hook failed");
-        CU(cudaMemcpyAsync(tot2, e->d_misc.p, 16, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
+    double tot2[2] = {0.0, 0.0};
+    for (rr_engine *s : sh) {
+        double p[2];
+        if ((rc = y_partial(e, s, 1, e->y_mean, p))) return rc;
+        tot2[0] += p[0];
+        tot2[1] += p[1];
     }
+    if ((rc = allreduce_small(e, tot2, 2))) return rc;
+    CU(cudaSetDevice(e->device));
     e->sum_yc = tot2[0];
     e->sst = tot2[1];
     e->sc.n_total = (double)e->n_total;
@@ -520,12 +762,19 @@ int compute_y_stats(rr_engine *e)
     return RR_OK;
 }
 
-int create_common(const double *Xsrc, const double *y, int64_t n, int32_t d, int32_t device, uint32_t flags,
-                  bool rowmajor, rr_engine **out)
+// what a shard ingests: rows of the caller's matrix (host, or device with RR_FLAG_X_DEVICE)
+struct Ingest {
+    const double *X = nullptr, *y = nullptr;
+    int64_t n_src = 0;        // rows of the caller's matrix
+    bool rowmajor = false;
+    const int32_t *pos = nullptr;  // host, n_src entries: engine row of each source row (-1: not selected); nullptr: identity
+    int64_t lo = 0, hi = 0;   // engine rows [lo, hi) belong to this shard
+};
+
+// One engine = one device = one block of rows. Nothing is synchronised against other shards here.
+int create_shard(const Ingest &in, int32_t d, int32_t device, uint32_t flags, rr_engine **out)
 {
-    if (!out) { g_thread_error = "out is null"; return RR_ERR_INVALID; }
     *out = nullptr;
-    if (!Xsrc || !y || n <= 0 || d <= 0) { g_thread_error = "rr_engine_create: bad arguments"; return RR_ERR_INVALID; }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
         g_thread_error = "no CUDA device: this engine has no CPU fallback";
@@ -539,6 +788,7 @@ int create_common(const double *Xsrc, const double *y, int64_t n, int32_t d, int
         g_thread_error = std::string("device ") + prop.name + " is not compute capability 10.x (sm_100a kernels only)";
         return RR_ERR_NO_DEVICE;
     }
+    const int64_t n = in.hi - in.lo;
     rr_engine *e = new rr_engine();
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
@@ -546,6 +796,7 @@ int create_common(const double *Xsrc, const double *y, int64_t n, int32_t d, int
     e->n = n;
     e->d = d;
     e->n_total = n;
+    e->n_object = n;
     e->ld = round_up(n, kLdAlign);
     e->exact_max_n = env_int("RR_B200_EXACT_MAX_N", 4096);
     e->s_pref = env_int("RR_B200_S", 0);
@@ -573,24 +824,162 @@ int create_common(const double *Xsrc, const double *y, int64_t n, int32_t d, int
     CUC(cudaMemsetAsync(e->X.p, 0, cols * e->ld * 8, e->stream));
     const bool on_dev = (flags & RR_FLAG_X_DEVICE) != 0;
     const cudaMemcpyKind kind = on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (!rowmajor) {
-        CUC(cudaMemcpy2DAsync(e->X.p, e->ld * 8, Xsrc, (size_t)n * 8, (size_t)n * 8, d, kind, e->stream));
+    double *ycol = e->X.as<double>() + (size_t)d * e->ld;
+    if (!in.rowmajor) {
+        // feature-major source: column j of the shard = rows [lo, hi) of column j (no index support: see the caller)
+        CUC(cudaMemcpy2DAsync(e->X.p, e->ld * 8, in.X + in.lo, (size_t)in.n_src * 8, (size_t)n * 8, d, kind, e->stream));
+        CUC(cudaMemcpyAsync(ycol, in.y + in.lo, (size_t)n * 8, kind, e->stream));
     } else {
-        const double *src = Xsrc;
+        // row-major source in row chunks: upload, then transpose (and scatter through the index) on the device.
+        // Without an index only this shard's rows are uploaded; with one every source row may land here.
+        const int64_t src0 = in.pos ? 0 : in.lo, src1 = in.pos ? in.n_src : in.hi;
+        const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(src1 - src0, (int64_t)(env_double("RR_B200_INGEST_CHUNK_BYTES", 256e6) / (8.0 * d))));
         if (!on_dev) {
-            CUC(e->d_V.ensure((size_t)n * d * 8));
-            CUC(cudaMemcpyAsync(e->d_V.p, Xsrc, (size_t)n * d * 8, cudaMemcpyHostToDevice, e->stream));
-            src = e->d_V.as<double>();
+            CUC(e->d_V.ensure((size_t)chunk * d * 8));
+            CUC(e->d_rhs.ensure((size_t)chunk * 8));
         }
-        dim3 grid((unsigned)((n + 31) / 32), (unsigned)((d + 31) / 32));
-        k_transpose_rowmajor<<<grid, dim3(32, 8), 0, e->stream>>>(src, n, d, e->X.as<double>(), e->ld);
-        CUC(cudaGetLastError());
+        if (in.pos) CUC(e->d_perm.ensure((size_t)chunk * 4));
+        for (int64_t r0 = src0; r0 < src1; r0 += chunk) {
+            const int64_t rows = std::min(chunk, src1 - r0);
+            const double *xsrc = in.X + (size_t)r0 * d, *ysrc = in.y + r0;
+            if (!on_dev) {
+                CUC(cudaMemcpyAsync(e->d_V.p, xsrc, (size_t)rows * d * 8, cudaMemcpyHostToDevice, e->stream));
+                CUC(cudaMemcpyAsync(e->d_rhs.p, ysrc, (size_t)rows * 8, cudaMemcpyHostToDevice, e->stream));
+                xsrc = e->d_V.as<double>();
+                ysrc = e->d_rhs.as<double>();
+            }
+            const int32_t *pos = nullptr;
+            if (in.pos) {
+                CUC(cudaMemcpyAsync(e->d_perm.p, in.pos + r0, (size_t)rows * 4, cudaMemcpyHostToDevice, e->stream));
+                pos = e->d_perm.as<int32_t>();
+            }
+            dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((d + 31) / 32));
+            k_ingest_rows<<<grid, dim3(32, 8), 0, e->stream>>>(xsrc, ysrc, rows, d, pos, r0, in.lo, in.hi, e->X.as<double>(), e->ld, ycol);
+            CUC(cudaGetLastError());
+            e->stats.kernel_launches++;
+        }
     }
-    CUC(cudaMemcpyAsync(e->X.as<double>() + (size_t)d * e->ld, y, (size_t)n * 8, kind, e->stream));
     CUC(cudaStreamSynchronize(e->stream));
-    const int rc = compute_y_stats(e);
-    if (rc) return bail(rc);
 #undef CUC
+    *out = e;
+    return RR_OK;
+}
+
+int create_common(const double *Xsrc, const double *y, int64_t n, int32_t d, int32_t device, uint32_t flags,
+                  bool rowmajor, rr_engine **out)
+{
+    if (!out) { g_thread_error = "out is null"; return RR_ERR_INVALID; }
+    *out = nullptr;
+    if (!Xsrc || !y || n <= 0 || d <= 0) { g_thread_error = "rr_engine_create: bad arguments"; return RR_ERR_INVALID; }
+    const auto t0 = std::chrono::steady_clock::now();
+    Ingest in;
+    in.X = Xsrc;
+    in.y = y;
+    in.n_src = n;
+    in.rowmajor = rowmajor;
+    in.lo = 0;
+    in.hi = n;
+    rr_engine *e = nullptr;
+    int rc = create_shard(in, d, device, flags, &e);
+    if (rc) return rc;
+    if ((rc = compute_y_stats(e))) {
+        g_thread_error = e->error;
+        e->free_all();
+        delete e;
+        return rc;
+    }
+    e->stats.ingest_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = e;
+    return RR_OK;
+}
+
+// rr_engine_create_sharded: n_gpus shards in this process, optional row selection
+int create_sharded(const double *Xsrc, const double *y, int64_t n_src, int32_t d, const int32_t *row_index, int64_t n_rows,
+                   int32_t n_gpus, uint32_t flags, rr_engine **out)
+{
+    if (!out) { g_thread_error = "out is null"; return RR_ERR_INVALID; }
+    *out = nullptr;
+    if (!Xsrc || !y || n_src <= 0 || d <= 0 || n_rows <= 0 || (!row_index && n_rows != n_src)) {
+        g_thread_error = "rr_engine_create_sharded: bad arguments";
+        return RR_ERR_INVALID;
+    }
+    const bool rowmajor = (flags & RR_FLAG_X_ROWMAJOR) != 0;
+    if (row_index && (!rowmajor || (flags & RR_FLAG_X_DEVICE))) {
+        g_thread_error = "rr_engine_create_sharded: a row index needs a row-major host matrix";
+        return RR_ERR_INVALID;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        g_thread_error = "no CUDA device: this engine has no CPU fallback";
+        return RR_ERR_NO_DEVICE;
+    }
+    int G = n_gpus <= 0 ? count : std::min<int>(n_gpus, count);
+    G = (int)std::max<int64_t>(1, std::min<int64_t>(G, n_rows / 1024));  // no shard below one tile's worth of rows
+    const auto t0 = std::chrono::steady_clock::now();
+    // engine row of every source row
+    std::vector<int32_t> pos;
+    if (row_index) {
+        pos.assign((size_t)n_src, -1);
+        for (int64_t i = 0; i < n_rows; ++i) {
+            const int32_t r = row_index[i];
+            if (r < 0 || r >= n_src) { g_thread_error = "rr_engine_create_sharded: row index out of range"; return RR_ERR_INVALID; }
+            pos[(size_t)r] = (int32_t)i;  // a row listed twice keeps its last position (the reference's index is a permutation)
+        }
+    }
+    std::vector<rr_engine *> sh;
+    auto bail = [&](int code) {
+        for (rr_engine *s : sh) {
+            cudaSetDevice(s->device);
+            s->free_all();
+            delete s;
+        }
+        return code;
+    };
+    int device0 = 0;
+    if (G == 1) cudaGetDevice(&device0);
+    for (int g = 0; g < G; ++g) {
+        Ingest in;
+        in.X = Xsrc;
+        in.y = y;
+        in.n_src = n_src;
+        in.rowmajor = rowmajor;
+        in.pos = row_index ? pos.data() : nullptr;
+        in.lo = n_rows * g / G;
+        in.hi = n_rows * (g + 1) / G;
+        rr_engine *s = nullptr;
+        const int rc = create_shard(in, d, G == 1 ? device0 : g, flags & ~(uint32_t)RR_FLAG_X_ROWMAJOR, &s);
+        if (rc) return bail(rc);
+        sh.push_back(s);
+    }
+    rr_engine *e = sh[0];
+    e->n_object = n_rows;
+    if (G > 1) {
+        std::lock_guard<std::mutex> lock(g_nccl_mu);
+        NcclApi &N = nccl();
+        if (!N.load()) { g_thread_error = N.err; return bail(RR_ERR_COLLECTIVE); }
+        std::vector<ncclComm_t> comms(G);
+        std::vector<int> devs(G);
+        for (int g = 0; g < G; ++g) devs[g] = sh[g]->device;
+        const ncclResult_t r = N.CommInitAll(comms.data(), G, devs.data());
+        if (r != ncclSuccess) { g_thread_error = std::string("ncclCommInitAll: ") + N.GetErrorString(r); return bail(RR_ERR_COLLECTIVE); }
+        for (int g = 0; g < G; ++g) {
+            sh[g]->comm = comms[g];
+            sh[g]->rank = g;
+            sh[g]->world = G;
+        }
+        e->peers.assign(sh.begin() + 1, sh.end());
+        cudaSetDevice(e->device);
+    }
+    const int rc = compute_y_stats(e);
+    if (rc) {
+        g_thread_error = e->error;
+        cudaSetDevice(e->device);
+        e->free_all();  // releases the peers too
+        delete e;
+        return rc;
+    }
+    e->n_total = n_rows;
+    e->stats.ingest_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = e;
     return RR_OK;
 }
@@ -635,7 +1024,7 @@ int run_eval(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     std::vector<int32_t> cand_dot;
     std::string err = bp.plan_eval(lim, cols, false, P, cand_dot);
     if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
-    int rc = run_sweep(e, P, S, e->d_dots, false, nullptr, 0);
+    int rc = run_sweep(e, P, S, &rr_engine::d_dots, false, nullptr, 0);
     if (rc) return rc;
     std::vector<double> dots(std::max(P.n_dots, 1));
     CU(cudaMemcpyAsync(dots.data(), e->d_dots.p, (size_t)P.n_dots * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -666,7 +1055,7 @@ int run_exact(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *
     int rc = ensure_result_buffers(e, nc, n_coef);
     if (rc) return rc;
     CU(e->d_V.ensure((size_t)std::max(bp.n_terms_distinct(), 1) * e->ld * 8));
-    rc = run_sweep(e, P, S, e->d_dots, false, e->d_V.as<double>(), e->ld);
+    rc = run_sweep(e, P, S, &rr_engine::d_dots, false, e->d_V.as<double>(), e->ld);
     if (rc) return rc;
     if ((rc = upload(e, e->d_ctb, b->cand_term_begin, (size_t)nc + 1))) return rc;
     if ((rc = upload(e, e->d_tid, bp.term_ids().data(), bp.term_ids().size()))) return rc;
@@ -760,7 +1149,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         err = bp.plan_gram(lim, cols, nullptr, false, P1, tab, tab_begin);
         if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
         phase("plan gram");
-        rc = run_sweep(e, P1, S, e->d_dots, false, nullptr, 0);
+        rc = run_sweep(e, P1, S, &rr_engine::d_dots, false, nullptr, 0);
         if (rc) return rc;
         phase("sweep gram");
     } else {
@@ -801,14 +1190,14 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
             if (threaded) planner2.join();
             return e->fail(RR_ERR_INVALID, err);
         }
-        rc = run_sweep(e, P1, S, e->d_dots, false, nullptr, 0, 0, 0, false);
+        rc = run_sweep(e, P1, S, &rr_engine::d_dots, false, nullptr, 0, 0, 0, false);
         if (threaded) planner2.join();
         else if (!rc) plan_second();
         if (rc) { cudaStreamSynchronize(e->stream); return rc; }
         if (!err2.empty()) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, err2); }
         const size_t off2 = (size_t)round_up(std::max(P1.n_dots, 1), 32);
         if (off2 + (size_t)P2.n_dots > tab_total + 256) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, "internal: dot vector too small"); }
-        rc = run_sweep(e, P2, S, e->d_dots, false, nullptr, 0, 1, off2, false);
+        rc = run_sweep(e, P2, S, &rr_engine::d_dots, false, nullptr, 0, 1, off2, false);
         if (rc) { cudaStreamSynchronize(e->stream); return rc; }
         const int32_t t0 = (int32_t)tab.size();
         for (int32_t id : tab2) tab.push_back(id + (int32_t)off2);
@@ -888,7 +1277,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         std::vector<int32_t> dtab, dtab_begin;
         err = bp.plan_gram(lim, cols, &escalate, true, Pd, dtab, dtab_begin);
         if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
-        rc = run_sweep(e, Pd, S, e->d_rdots, true, nullptr, 0);
+        rc = run_sweep(e, Pd, S, &rr_engine::d_rdots, true, nullptr, 0);
         if (rc) return rc;
         DevBuf &d_dt = e->d_t0, &d_dtb = e->d_t1, &d_l = e->d_t2, &d_wo = e->d_t3;
         auto cleanup = [&]() {};
@@ -947,7 +1336,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         std::vector<int32_t> rtab, rtab_begin;
         err = bp.plan_residual(lim, cols, ok, cs.data(), Pr, rtab, rtab_begin);
         if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
-        rc = run_sweep(e, Pr, S, e->d_rdots, false, nullptr, 0);
+        rc = run_sweep(e, Pr, S, &rr_engine::d_rdots, false, nullptr, 0);
         if (rc) return rc;
         // split `ok` back into refine (pending) and escalated members, keeping residual-table offsets
         std::vector<int32_t> l_ref, l_esc, rb_ref, rb_esc;
@@ -1012,89 +1401,131 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
-extern "C" {
+namespace {
 
-int rr_abi_version(void) { return RR_ABI_VERSION; }
-
-const char *rr_last_error(const rr_engine *e) { return e ? e->error.c_str() : g_thread_error.c_str(); }
-
-int rr_engine_create(const double *X, const double *y, int64_t n, int32_t d, int32_t device, uint32_t flags,
-                     rr_engine **out)
+// predict(): the program is planned once (materialising plan: interpreter + RI_STG epilogue) and the caller's
+// matrix is streamed through the engine in row chunks - upload, transpose on the device when it is row-major, sweep,
+// download - on the engine's own stream and grow-only buffers; the chunks of a multi-GPU engine go round the shards.
+// No engine is created, no target statistics are computed, nothing of the resident data set is touched.
+int predict_impl(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts, int32_t n_consts,
+                 const double *X, int64_t n, int32_t d, bool rowmajor, bool proba, double *out)
 {
-    return create_common(X, y, n, d, device, flags, false, out);
-}
-
-int rr_engine_create_rowmajor(const double *X, const double *y, int64_t n, int32_t d, int32_t device, uint32_t flags,
-                              rr_engine **out)
-{
-    return create_common(X, y, n, d, device, flags, true, out);
-}
-
-void rr_engine_destroy(rr_engine *e)
-{
-    if (!e) return;
+    if (!e) { g_thread_error = "null engine"; return RR_ERR_INVALID; }
+    if (!code || code_len <= 0 || !X || !out || n <= 0 || d <= 0) return e->fail(RR_ERR_INVALID, "rr_predict: bad arguments");
+    int32_t ctb[2] = {0, 1}, tcb[2] = {0, code_len};
+    rr_batch b;
+    std::memset(&b, 0, sizeof(b));
+    b.mode = RR_MODE_EVAL_ONLY;
+    b.n_cand = 1;
+    b.cand_term_begin = ctb;
+    b.term_code_begin = tcb;
+    b.code = code;
+    b.consts = consts;
+    b.n_consts = n_consts;
+    b.n_code = code_len;
+    rr::BatchPlanner bp(&b, d);
+    std::string err = bp.analyse(true);
+    if (!err.empty()) return e->fail(RR_ERR_INVALID, "rr_predict: " + err);
+    const int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(4096, (int64_t)(env_double("RR_B200_PREDICT_CHUNK_BYTES", 128e6) / (8.0 * d))));
+    // launch shape for the chunk height (the engine's own shape follows its resident n)
+    SweepCfg S;
+    {
+        rr_engine probe;  // only the fields choose_cfg reads
+        probe.n = chunk;
+        probe.d = d;
+        probe.s_pref = e->s_pref;
+        probe.th_pref = e->th_pref;
+        probe.occ_pref = e->occ_pref;
+        probe.d_misc = e->d_misc;
+        probe.stream = e->stream;
+        CU(cudaSetDevice(e->device));
+        S = choose_cfg(&probe);
+        e->d_misc = probe.d_misc;  // the probe may have grown the shared scratch buffer
+        probe.d_misc = DevBuf();
+        probe.stream = nullptr;
+    }
+    rr::PlanLimits lim;
+    lim.tile_cols = S.tile_cols();
+    lim.no_cse = true;
+    lim.fuse = env_int("RR_B200_FUSE", 1) != 0;
+    lim.mdot_rows = S.S == 4 && S.TH == 128;
+    lim.target_chunks = 1;
+    rr::SweepPlan P;
+    err = bp.plan_materialise(lim, rr::ColIds{d, d + 1}, P);
+    if (!err.empty()) return e->fail(RR_ERR_INVALID, "rr_predict: " + err);
+    std::vector<RRIns> ins(P.ins);
+    RRIns endi;
+    std::memset(&endi, 0, sizeof(endi));
+    ins.resize(P.ins.size() + rr::kInsWindow, endi);
+    std::vector<rr_engine *> sh = shards_of(e);
+    const int64_t ldc = round_up(chunk, kLdAlign);
+    int rc = RR_OK;
+    int64_t ci = 0;
+    for (int64_t r0 = 0; r0 < n && !rc; r0 += chunk, ++ci) {
+        rr_engine *s = sh[(size_t)(ci % (int64_t)sh.size())];
+        const int64_t rows = std::min(chunk, n - r0);
+        CU(cudaSetDevice(s->device));
+        CU(s->d_px.ensure((size_t)d * ldc * 8));
+        CU(s->d_pout.ensure((size_t)ldc * 8 * (proba ? 3 : 1)));
+        // columns are read in whole tiles: the tail beyond `rows` must hold finite numbers
+        CU(cudaMemsetAsync(s->d_px.p, 0, (size_t)d * ldc * 8, s->stream));
+        if (rowmajor) {
+            CU(s->d_pr.ensure((size_t)chunk * d * 8));
+            CU(cudaMemcpyAsync(s->d_pr.p, X + (size_t)r0 * d, (size_t)rows * d * 8, cudaMemcpyHostToDevice, s->stream));
+            dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((d + 31) / 32));
+            k_ingest_rows<<<grid, dim3(32, 8), 0, s->stream>>>(s->d_pr.as<double>(), nullptr, rows, d, nullptr, 0, 0, rows,
+                                                              s->d_px.as<double>(), ldc, nullptr);
+            CU(cudaGetLastError());
+            e->stats.kernel_launches++;
+        } else {
+            CU(cudaMemcpy2DAsync(s->d_px.p, (size_t)ldc * 8, X + r0, (size_t)n * 8, (size_t)rows * 8, d, cudaMemcpyHostToDevice, s->stream));
+        }
+        const XView view{s->d_px.as<double>(), ldc, rows};
+        rc = launch_shard(e, s, P, ins, S, view, &rr_engine::d_dots, false, s->d_pout.as<double>(), ldc, 0, 0);
+        if (rc) break;
+        if (proba) {
+            k_proba<<<(unsigned)((rows + 255) / 256), 256, 0, s->stream>>>(s->d_pout.as<double>(), rows, s->d_pout.as<double>() + ldc);
+            CU(cudaGetLastError());
+            e->stats.kernel_launches++;
+            CU(cudaMemcpyAsync(out + 2 * r0, s->d_pout.as<double>() + ldc, (size_t)rows * 16, cudaMemcpyDeviceToHost, s->stream));
+        } else {
+            CU(cudaMemcpyAsync(out + r0, s->d_pout.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, s->stream));
+        }
+    }
+    for (rr_engine *s : sh) {
+        cudaSetDevice(s->device);
+        const cudaError_t ce = cudaStreamSynchronize(s->stream);
+        if (ce != cudaSuccess && !rc) rc = e->cuda_fail(ce, "rr_predict");
+    }
     cudaSetDevice(e->device);
-    e->free_all();
-    delete e;
+    return rc;
 }
 
-int rr_engine_set_allreduce(rr_engine *e, rr_allreduce_fn fn, void *user, int32_t rank, int32_t world)
-{
-    if (!e) return RR_ERR_INVALID;
-    if (world < 1 || rank < 0 || rank >= world) return e->fail(RR_ERR_INVALID, "bad rank/world");
-    CU(cudaSetDevice(e->device));
-    e->allreduce = fn;
-    e->allreduce_user = user;
-    e->rank = rank;
-    e->world = fn ? world : 1;
-    return compute_y_stats(e);
-}
-
-int rr_engine_get_info(const rr_engine *e, rr_engine_info *info)
-{
-    if (!e || !info) return RR_ERR_INVALID;
-    info->n = e->n;
-    info->n_total = e->n_total;
-    info->d = e->d;
-    info->device = e->device;
-    info->y_mean = e->y_mean;
-    info->sst = e->sst;
-    info->sm_count = e->sm_count;
-    info->exact_max_n = e->exact_max_n;
-    return RR_OK;
-}
-
-int rr_get_stats(const rr_engine *e, rr_stats *stats)
-{
-    if (!e || !stats) return RR_ERR_INVALID;
-    *stats = e->stats;
-    return RR_OK;
-}
-
-int rr_score_batch(rr_engine *e, const rr_batch *b, rr_result *res)
+int score_batch_impl(rr_engine *e, const rr_batch *b, rr_result *res)
 {
     if (!e) { g_thread_error = "null engine"; return RR_ERR_INVALID; }
     if (!b || !res || !res->ssr) return e->fail(RR_ERR_INVALID, "null batch/result (result.ssr is required)");
     if (b->mode != RR_MODE_EVAL_ONLY && b->mode != RR_MODE_OLS_FIT) return e->fail(RR_ERR_INVALID, "bad mode");
+    if (b->n_cand < 0) return e->fail(RR_ERR_INVALID, "malformed batch: negative candidate count");
     if (b->n_cand == 0) return RR_OK;
+    const auto t_host0 = std::chrono::steady_clock::now();
     CU(cudaSetDevice(e->device));
+    // the device clock of the batch starts before the host-side analysis: `last_batch_ms` is what a caller waits for
+    CU(cudaEventRecord(e->ev[0], e->stream));
     rr::BatchPlanner bp(b, e->d);
     std::string err = bp.analyse((e->flags & RR_FLAG_NO_CSE) != 0);
     if (!err.empty()) return e->fail(RR_ERR_INVALID, "malformed batch: " + err);
     e->stats.h2d_bytes = e->stats.d2h_bytes = 0;
     e->stats.w_shared = 0.0;
     e->sweep_ms_accum = 0.f;
-    const uint64_t dd0 = e->stats.distinct_dots;
-    (void)dd0;
-    CU(cudaEventRecord(e->ev[0], e->stream));
     int rc;
     if (b->mode == RR_MODE_EVAL_ONLY) {
         rc = run_eval(e, b, bp, res);
     } else {
-        const bool sharded = e->allreduce && e->world > 1;
-        bool exact = !sharded && e->n_total <= e->exact_max_n;
+        const bool split = e->rows_split();
+        bool exact = !split && e->n_total <= e->exact_max_n;
         if (e->flags & RR_FLAG_FORCE_GRAM) exact = false;
-        if ((e->flags & RR_FLAG_FORCE_EXACT) && !sharded) exact = true;
+        if ((e->flags & RR_FLAG_FORCE_EXACT) && !split) exact = true;
         rc = exact ? run_exact(e, b, bp, res) : run_gram(e, b, bp, res);
     }
     if (rc) return rc;
@@ -1104,6 +1535,7 @@ int rr_score_batch(rr_engine *e, const rr_batch *b, rr_result *res)
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
     e->stats.last_batch_ms = ms;
     e->stats.last_sweep_ms = e->sweep_ms_accum;
+    e->stats.last_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     e->stats.batches++;
     e->stats.candidates += b->n_cand;
     e->stats.term_instances += bp.n_term_instances();
@@ -1123,10 +1555,11 @@ int rr_score_batch(rr_engine *e, const rr_batch *b, rr_result *res)
     return RR_OK;
 }
 
-int rr_classifier_metrics(rr_engine *e, const rr_batch *b, double *accuracy, double *log_loss, double *abs_loss)
+int classifier_metrics_impl(rr_engine *e, const rr_batch *b, double *accuracy, double *log_loss, double *abs_loss)
 {
     if (!e) { g_thread_error = "null engine"; return RR_ERR_INVALID; }
     if (!b || b->mode != RR_MODE_EVAL_ONLY) return e->fail(RR_ERR_INVALID, "classifier metrics need an EVAL_ONLY batch");
+    if (b->n_cand < 0) return e->fail(RR_ERR_INVALID, "malformed batch: negative candidate count");
     if (b->n_cand == 0) return RR_OK;
     CU(cudaSetDevice(e->device));
     rr::BatchPlanner bp(b, e->d);
@@ -1139,7 +1572,7 @@ int rr_classifier_metrics(rr_engine *e, const rr_batch *b, double *accuracy, dou
     std::vector<int32_t> cand_dot;
     err = bp.plan_eval(lim, cols, true, P, cand_dot);
     if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
-    int rc = run_sweep(e, P, S, e->d_dots, false, nullptr, 0);
+    int rc = run_sweep(e, P, S, &rr_engine::d_dots, false, nullptr, 0);
     if (rc) return rc;
     std::vector<double> dots(std::max(P.n_dots, 1));
     CU(cudaMemcpyAsync(dots.data(), e->d_dots.p, (size_t)P.n_dots * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -1154,65 +1587,231 @@ int rr_classifier_metrics(rr_engine *e, const rr_batch *b, double *accuracy, dou
     return RR_OK;
 }
 
-static int predict_common(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts, int32_t n_consts,
-                          const double *X, int64_t n, int32_t d, bool rowmajor, double *out)
+int feature_r2_impl(rr_engine *e, double *r2)
+{
+    if (!e || !r2) { g_thread_error = "rr_feature_r2: null argument"; return RR_ERR_INVALID; }
+    if (e->sharded()) return e->fail(RR_ERR_INVALID, "rr_feature_r2: not available on a rank of a multi-process engine");
+    const int blocks = 64, d = e->d;
+    std::vector<rr_engine *> sh = shards_of(e);
+    std::vector<double> part((size_t)d * blocks * 2), sum(d, 0.0), mean(d), sst(d, 0.0), ssr(d, 0.0);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (rr_engine *s : sh) {
+            CU(cudaSetDevice(s->device));
+            CU(s->d_aux.ensure((size_t)d * blocks * 2 * 8 + (size_t)d * 8));
+            double *d_part = s->d_aux.as<double>(), *d_mean = d_part + (size_t)d * blocks * 2;
+            if (pass) CU(cudaMemcpyAsync(d_mean, mean.data(), (size_t)d * 8, cudaMemcpyHostToDevice, s->stream));
+            k_feature_stats<<<dim3(blocks, d), 256, 0, s->stream>>>(s->X.as<double>(), s->ld, s->X.as<double>() + (size_t)d * s->ld, s->n,
+                                                                   d_mean, pass, d_part);
+            CU(cudaGetLastError());
+            e->stats.kernel_launches++;
+            CU(cudaMemcpyAsync(part.data(), d_part, part.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            for (int j = 0; j < d; ++j)
+                for (int bi = 0; bi < blocks; ++bi) {
+                    const double a = part[2 * ((size_t)j * blocks + bi)], b2 = part[2 * ((size_t)j * blocks + bi) + 1];
+                    if (pass == 0) sum[j] += a;
+                    else { sst[j] += a; ssr[j] += b2; }
+                }
+        }
+        if (pass == 0)
+            for (int j = 0; j < d; ++j) mean[j] = sum[j] / (double)e->n_object;
+    }
+    CU(cudaSetDevice(e->device));
+    for (int j = 0; j < d; ++j) r2[j] = 1 - ssr[j] / sst[j];  // R2(X[j], y), rils_rols_cpp.cpp:40-45 with :763's argument order
+    return RR_OK;
+}
+
+int read_rows_impl(rr_engine *e, int64_t row0, int64_t rows, double *Xout, double *yout)
 {
     if (!e) { g_thread_error = "null engine"; return RR_ERR_INVALID; }
-    if (!code || code_len <= 0 || !X || !out || n <= 0 || d <= 0) return e->fail(RR_ERR_INVALID, "rr_predict: bad arguments");
-    // a temporary engine over the caller's matrix (y is a dummy column) shares the kernels
-    std::vector<double> ydummy((size_t)n, 0.0);
-    rr_engine *t = nullptr;
-    int rc = create_common(X, ydummy.data(), n, d, e->device, 0, rowmajor, &t);
-    if (rc) return e->fail(rc, g_thread_error);
-    int32_t ctb[2] = {0, 1}, tcb[2] = {0, code_len};
-    rr_batch b;
-    std::memset(&b, 0, sizeof(b));
-    b.mode = RR_MODE_EVAL_ONLY;
-    b.n_cand = 1;
-    b.cand_term_begin = ctb;
-    b.term_code_begin = tcb;
-    b.code = code;
-    b.consts = consts;
-    b.n_consts = n_consts;
-    rr::BatchPlanner bp(&b, d);
-    std::string err = bp.analyse(true);
-    if (err.empty()) {
-        const SweepCfg S = choose_cfg(t);
-        rr::PlanLimits lim = limits_for(t, S, 1);
-        lim.target_chunks = 1;
-        rr::SweepPlan P;
-        err = bp.plan_materialise(lim, rr::ColIds{d, d + 1}, P);
-        if (err.empty()) {
-            cudaError_t ce = t->d_V.ensure((size_t)t->ld * 8);
-            if (ce != cudaSuccess) err = cudaGetErrorString(ce);
-            if (err.empty()) {
-                rc = run_sweep(t, P, S, t->d_dots, false, t->d_V.as<double>(), t->ld);
-                if (rc) err = t->error;
-            }
-            if (err.empty()) {
-                ce = cudaMemcpyAsync(out, t->d_V.p, (size_t)n * 8, cudaMemcpyDeviceToHost, t->stream);
-                if (ce == cudaSuccess) ce = cudaStreamSynchronize(t->stream);
-                if (ce != cudaSuccess) err = cudaGetErrorString(ce);
-            }
+    if (row0 < 0 || rows <= 0 || row0 + rows > e->n_object) return e->fail(RR_ERR_INVALID, "rr_engine_read_rows: range");
+    int64_t base = 0;
+    for (rr_engine *s : shards_of(e)) {
+        const int64_t lo = std::max(row0, base), hi = std::min(row0 + rows, base + s->n);
+        if (lo < hi) {
+            CU(cudaSetDevice(s->device));
+            if (Xout)
+                CU(cudaMemcpy2DAsync(Xout + (lo - row0), (size_t)rows * 8, s->X.as<double>() + (lo - base), (size_t)s->ld * 8, (size_t)(hi - lo) * 8,
+                                     s->d, cudaMemcpyDeviceToHost, s->stream));
+            if (yout)
+                CU(cudaMemcpyAsync(yout + (lo - row0), s->X.as<double>() + (size_t)s->d * s->ld + (lo - base), (size_t)(hi - lo) * 8,
+                                   cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
         }
+        base += s->n;
     }
-    e->stats.kernel_launches += t->stats.kernel_launches;
-    e->stats.sweep_launches += t->stats.sweep_launches;
-    rr_engine_destroy(t);
-    if (!err.empty()) return e->fail(RR_ERR_INVALID, "rr_predict: " + err);
+    CU(cudaSetDevice(e->device));
     return RR_OK;
+}
+
+// No C++ exception crosses the C boundary: allocation failures and anything else thrown by the planner or the
+// standard library become return codes.
+template <typename F> int guarded(rr_engine *e, F &&f)
+{
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        if (e) e->error = "out of host memory";
+        else g_thread_error = "out of host memory";
+        return RR_ERR_NOMEM;
+    } catch (const std::exception &ex) {
+        if (e) e->error = std::string("internal error: ") + ex.what();
+        else g_thread_error = std::string("internal error: ") + ex.what();
+        return RR_ERR_INVALID;
+    } catch (...) {
+        if (e) e->error = "internal error";
+        else g_thread_error = "internal error";
+        return RR_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rr_abi_version(void) { return RR_ABI_VERSION; }
+
+const char *rr_last_error(const rr_engine *e) { return e ? e->error.c_str() : g_thread_error.c_str(); }
+
+int rr_engine_create(const double *X, const double *y, int64_t n, int32_t d, int32_t device, uint32_t flags,
+                     rr_engine **out)
+{
+    return guarded(nullptr, [&] { return create_common(X, y, n, d, device, flags, false, out); });
+}
+
+int rr_engine_create_rowmajor(const double *X, const double *y, int64_t n, int32_t d, int32_t device, uint32_t flags,
+                              rr_engine **out)
+{
+    return guarded(nullptr, [&] { return create_common(X, y, n, d, device, flags, true, out); });
+}
+
+int rr_engine_create_sharded(const double *X, const double *y, int64_t n, int32_t d, const int32_t *row_index, int64_t n_rows,
+                             int32_t n_gpus, uint32_t flags, rr_engine **out)
+{
+    return guarded(nullptr, [&] { return create_sharded(X, y, n, d, row_index, n_rows, n_gpus, flags, out); });
+}
+
+void rr_engine_destroy(rr_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    e->free_all();
+    delete e;
+}
+
+int rr_comm_unique_id(void *id128)
+{
+    if (!id128) { g_thread_error = "rr_comm_unique_id: null"; return RR_ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    NcclApi &N = nccl();
+    if (!N.load()) { g_thread_error = N.err; return RR_ERR_COLLECTIVE; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    const ncclResult_t r = N.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_thread_error = std::string("ncclGetUniqueId: ") + N.GetErrorString(r); return RR_ERR_COLLECTIVE; }
+    std::memcpy(id128, &id, 128);
+    return RR_OK;
+}
+
+int rr_engine_comm_init(rr_engine *e, const void *id128, int32_t rank, int32_t world)
+{
+    if (!e) { g_thread_error = "null engine"; return RR_ERR_INVALID; }
+    if (!id128 || world < 1 || rank < 0 || rank >= world) return e->fail(RR_ERR_INVALID, "bad rank/world");
+    if (e->grouped()) return e->fail(RR_ERR_INVALID, "this engine already shards its rows over its own devices");
+    return guarded(e, [&]() -> int {
+        NcclApi &N = nccl();
+        {
+            std::lock_guard<std::mutex> lock(g_nccl_mu);
+            if (!N.load()) return e->fail(RR_ERR_COLLECTIVE, N.err);
+        }
+        CU(cudaSetDevice(e->device));
+        if (e->comm) { N.CommDestroy(e->comm); e->comm = nullptr; }
+        ncclUniqueId id;
+        std::memcpy(&id, id128, 128);
+        NC(N.CommInitRank(&e->comm, world, id, rank));
+        e->allreduce = nullptr;
+        e->comm_ranks = true;
+        e->rank = rank;
+        e->world = world;
+        return compute_y_stats(e);
+    });
+}
+
+int rr_engine_set_allreduce(rr_engine *e, rr_allreduce_fn fn, void *user, int32_t rank, int32_t world)
+{
+    if (!e) return RR_ERR_INVALID;
+    if (world < 1 || rank < 0 || rank >= world) return e->fail(RR_ERR_INVALID, "bad rank/world");
+    if (e->grouped()) return e->fail(RR_ERR_INVALID, "this engine already shards its rows over its own devices");
+    return guarded(e, [&]() -> int {
+        CU(cudaSetDevice(e->device));
+        if (e->comm) { nccl().CommDestroy(e->comm); e->comm = nullptr; e->comm_ranks = false; }
+        e->allreduce = fn;
+        e->allreduce_user = user;
+        e->rank = rank;
+        e->world = fn ? world : 1;
+        return compute_y_stats(e);
+    });
+}
+
+int rr_engine_get_info(const rr_engine *e, rr_engine_info *info)
+{
+    if (!e || !info) return RR_ERR_INVALID;
+    info->n = e->n_object;
+    info->n_total = e->n_total;
+    info->d = e->d;
+    info->device = e->device;
+    info->y_mean = e->y_mean;
+    info->sst = e->sst;
+    info->sm_count = e->sm_count;
+    info->exact_max_n = e->exact_max_n;
+    info->n_gpus = 1 + (int32_t)e->peers.size();
+    info->world = e->world;
+    return RR_OK;
+}
+
+int rr_get_stats(const rr_engine *e, rr_stats *stats)
+{
+    if (!e || !stats) return RR_ERR_INVALID;
+    *stats = e->stats;
+    return RR_OK;
+}
+
+int rr_score_batch(rr_engine *e, const rr_batch *b, rr_result *res)
+{
+    return guarded(e, [&] { return score_batch_impl(e, b, res); });
+}
+
+int rr_classifier_metrics(rr_engine *e, const rr_batch *b, double *accuracy, double *log_loss, double *abs_loss)
+{
+    return guarded(e, [&] { return classifier_metrics_impl(e, b, accuracy, log_loss, abs_loss); });
 }
 
 int rr_predict(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts, int32_t n_consts,
                const double *X, int64_t n, int32_t d, double *out)
 {
-    return predict_common(e, code, code_len, consts, n_consts, X, n, d, false, out);
+    return guarded(e, [&] { return predict_impl(e, code, code_len, consts, n_consts, X, n, d, false, false, out); });
 }
 
 int rr_predict_rowmajor(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts, int32_t n_consts,
                         const double *X, int64_t n, int32_t d, double *out)
 {
-    return predict_common(e, code, code_len, consts, n_consts, X, n, d, true, out);
+    return guarded(e, [&] { return predict_impl(e, code, code_len, consts, n_consts, X, n, d, true, false, out); });
+}
+
+int rr_predict_proba_rowmajor(rr_engine *e, const uint32_t *code, int32_t code_len, const double *consts, int32_t n_consts,
+                              const double *X, int64_t n, int32_t d, double *out)
+{
+    return guarded(e, [&] { return predict_impl(e, code, code_len, consts, n_consts, X, n, d, true, true, out); });
+}
+
+int rr_feature_r2(rr_engine *e, double *r2)
+{
+    return guarded(e, [&] { return feature_r2_impl(e, r2); });
+}
+
+int rr_engine_read_rows(rr_engine *e, int64_t row0, int64_t rows, double *Xout, double *yout)
+{
+    return guarded(e, [&] { return read_rows_impl(e, row0, rows, Xout, yout); });
 }
 
 int rr_measure_fp64_peak(rr_engine *e, double *dfma_per_second)

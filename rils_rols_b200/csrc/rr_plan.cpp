@@ -283,8 +283,15 @@ std::string BatchPlanner::analyse(bool no_cse)
     if (b_->n_cand == 0) return "";
     if (!b_->cand_term_begin || !b_->term_code_begin) return "null batch arrays";
     const int32_t n_terms = b_->cand_term_begin[b_->n_cand];
+    if (n_terms < 0) return "negative term count";
     if (n_terms > 0 && !b_->code) return "null batch arrays";  // a batch of term-less candidates has no code
     if (b_->cand_term_begin[0] != 0 || b_->term_code_begin[0] != 0) return "offset arrays must start at 0";
+    for (int32_t c = 0; c < b_->n_cand; ++c)
+        if (b_->cand_term_begin[c + 1] < b_->cand_term_begin[c]) return "candidate offsets must not decrease";
+    if (b_->n_consts < 0 || (b_->n_consts > 0 && !b_->consts)) return "bad constant pool";
+    if (b_->n_code < 0) return "negative code length";
+    // with the code length known (ABI 2) every term's range is checked against it; without it only monotony can be
+    if (b_->n_code > 0 && n_terms > 0 && b_->term_code_begin[n_terms] > b_->n_code) return "term offsets exceed the code length";
     term_id_.assign(n_terms, -1);
     terms_.clear();
     CodeTable seen(b_, (size_t)n_terms / 4 + 64);

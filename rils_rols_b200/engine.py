@@ -18,10 +18,13 @@ LIB_PATH = os.path.join(_HERE, "librr_b200.so")
 _LIB: Optional[C.CDLL] = None
 
 EXPORTS = [
-    "rr_abi_version", "rr_last_error", "rr_engine_create", "rr_engine_create_rowmajor", "rr_engine_destroy",
-    "rr_engine_set_allreduce", "rr_engine_get_info", "rr_get_stats", "rr_score_batch", "rr_classifier_metrics",
-    "rr_predict", "rr_predict_rowmajor", "rr_measure_fp64_peak",
+    "rr_abi_version", "rr_last_error", "rr_engine_create", "rr_engine_create_rowmajor", "rr_engine_create_sharded",
+    "rr_engine_destroy", "rr_comm_unique_id", "rr_engine_comm_init", "rr_engine_set_allreduce", "rr_engine_get_info",
+    "rr_get_stats", "rr_score_batch", "rr_classifier_metrics", "rr_predict", "rr_predict_rowmajor",
+    "rr_predict_proba_rowmajor", "rr_feature_r2", "rr_engine_read_rows", "rr_measure_fp64_peak",
+    "rr_debug_plan_batch", "rr_debug_plan_free", "rr_debug_plan_concurrency_check",
 ]
+ABI_VERSION = 2
 
 
 class EngineError(RuntimeError):
@@ -30,7 +33,8 @@ class EngineError(RuntimeError):
 
 class rr_engine_info(C.Structure):
     _fields_ = [("n", C.c_int64), ("n_total", C.c_int64), ("d", C.c_int32), ("device", C.c_int32),
-                ("y_mean", C.c_double), ("sst", C.c_double), ("sm_count", C.c_int32), ("exact_max_n", C.c_int32)]
+                ("y_mean", C.c_double), ("sst", C.c_double), ("sm_count", C.c_int32), ("exact_max_n", C.c_int32),
+                ("n_gpus", C.c_int32), ("world", C.c_int32)]
 
 
 class rr_stats(C.Structure):
@@ -39,7 +43,8 @@ class rr_stats(C.Structure):
                 ("nonfinite", C.c_uint64), ("distinct_terms", C.c_uint64), ("term_instances", C.c_uint64),
                 ("distinct_dots", C.c_uint64), ("dot_instances", C.c_uint64), ("last_sweep_ms", C.c_double),
                 ("last_batch_ms", C.c_double), ("w_contract", C.c_double), ("w_shared", C.c_double),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("last_host_ms", C.c_double),
+                ("ingest_ms", C.c_double), ("collectives", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -66,8 +71,14 @@ def lib() -> C.CDLL:
         f = getattr(L, name)
         f.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(vp)]
         f.restype = C.c_int
+    L.rr_engine_create_sharded.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, C.c_int64, C.c_int32, C.c_uint32, C.POINTER(vp)]
+    L.rr_engine_create_sharded.restype = C.c_int
     L.rr_engine_destroy.argtypes = [vp]
     L.rr_engine_destroy.restype = None
+    L.rr_comm_unique_id.argtypes = [vp]
+    L.rr_comm_unique_id.restype = C.c_int
+    L.rr_engine_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.rr_engine_comm_init.restype = C.c_int
     L.rr_engine_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp, C.c_int32, C.c_int32]
     L.rr_engine_set_allreduce.restype = C.c_int
     L.rr_engine_get_info.argtypes = [vp, C.POINTER(rr_engine_info)]
@@ -82,6 +93,12 @@ def lib() -> C.CDLL:
         f = getattr(L, name)
         f.argtypes = [vp, up, C.c_int32, dp, C.c_int32, dp, C.c_int64, C.c_int32, dp]
         f.restype = C.c_int
+    L.rr_predict_proba_rowmajor.argtypes = [vp, up, C.c_int32, dp, C.c_int32, dp, C.c_int64, C.c_int32, dp]
+    L.rr_predict_proba_rowmajor.restype = C.c_int
+    L.rr_feature_r2.argtypes = [vp, dp]
+    L.rr_feature_r2.restype = C.c_int
+    L.rr_engine_read_rows.argtypes = [vp, C.c_int64, C.c_int64, vp, vp]
+    L.rr_engine_read_rows.restype = C.c_int
     L.rr_measure_fp64_peak.argtypes = [vp, dp]
     L.rr_measure_fp64_peak.restype = C.c_int
     _LIB = L
@@ -116,6 +133,34 @@ class Engine:
             raise EngineError(f"rr_engine_create failed ({rc}): {L.rr_last_error(None).decode()}")
         self.n, self.d = int(n), int(d)
         self._cb = None
+
+    @classmethod
+    def sharded(cls, X: np.ndarray, y: np.ndarray, n_gpus: int = 0, row_index: Optional[np.ndarray] = None,
+                rowmajor: bool = True, flags: int = 0) -> "Engine":
+        """ONE engine object over n_gpus devices of this process (0 = all visible): rows in contiguous blocks,
+        NCCL inside the engine (rr_engine_create_sharded). row_index selects and orders the rows on the device
+        (the shuffle / sub-sample of rils_rols_cpp.cpp:774-795)."""
+        from .batch import FLAG_X_ROWMAJOR
+
+        L = lib()
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        n, d = (X.shape if rowmajor else X.shape[::-1])
+        if y.shape[0] != n:
+            raise ValueError(f"Size of y {y.shape[0]} is not the same as the data count {n}")
+        idx, n_rows = None, n
+        if row_index is not None:
+            idx = np.ascontiguousarray(row_index, dtype=np.int32)
+            n_rows = int(idx.size)
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        rc = L.rr_engine_create_sharded(X.ctypes.data, y.ctypes.data, n, d, idx.ctypes.data if idx is not None else None,
+                                        n_rows, n_gpus, flags | (FLAG_X_ROWMAJOR if rowmajor else 0), C.byref(self._h))
+        if rc != 0:
+            raise EngineError(f"rr_engine_create_sharded failed ({rc}): {L.rr_last_error(None).decode()}")
+        self.n, self.d = int(n_rows), int(d)
+        self._cb = None
+        return self
 
     @classmethod
     def from_device(cls, x_ptr: int, y_ptr: int, n: int, d: int, device: int = -1, flags: int = 0) -> "Engine":
@@ -188,6 +233,49 @@ class Engine:
         self._check(fn(self._h, code.ctypes.data_as(C.POINTER(C.c_uint32)), code.size, _dp(k), consts.size, _dp(X),
                        n, d, _dp(out)), "rr_predict")
         return out
+
+    def predict_proba(self, code: np.ndarray, consts: np.ndarray, X: np.ndarray) -> np.ndarray:
+        """(n, 2) array [1 - p, p], p = logistic(2 (yhat - 0.5)) (rr_predict_proba_rowmajor)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        n, d = X.shape
+        code = np.ascontiguousarray(code, dtype=np.uint32)
+        consts = np.ascontiguousarray(consts, dtype=np.float64)
+        k = consts if consts.size else np.zeros(1)
+        out = np.empty((n, 2))
+        self._check(lib().rr_predict_proba_rowmajor(self._h, code.ctypes.data_as(C.POINTER(C.c_uint32)), code.size, _dp(k),
+                                                    consts.size, _dp(X), n, d, _dp(out)), "rr_predict_proba")
+        return out
+
+    def feature_r2(self) -> np.ndarray:
+        """R2(X[j], y) of relevant_features(), rils_rols_cpp.cpp:753-770, for every feature (one device reduction)."""
+        out = np.empty(self.d)
+        self._check(lib().rr_feature_r2(self._h, _dp(out)), "rr_feature_r2")
+        return out
+
+    def read_rows(self, row0: int, rows: int):
+        """(X feature-major (d, rows), y) of the engine's resident rows [row0, row0 + rows)."""
+        X = np.empty((self.d, rows))
+        y = np.empty(rows)
+        self._check(lib().rr_engine_read_rows(self._h, row0, rows, X.ctypes.data, y.ctypes.data), "rr_engine_read_rows")
+        return X, y
+
+    def comm_init_torch(self, group=None):
+        """One process per GPU: NCCL INSIDE the engine. Rank 0 draws the unique id, torch.distributed only carries
+        its 128 bytes to the other ranks; every later all-reduce is issued by the engine itself on its own stream
+        (no Python, no host synchronisation in the step)."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            rc = lib().rr_comm_unique_id(buf)
+            if rc != 0:
+                raise EngineError(f"rr_comm_unique_id failed ({rc}): {lib().rr_last_error(None).decode()}")
+        obj = [bytes(buf)]
+        dist.broadcast_object_list(obj, src=0, group=group)
+        raw = (C.c_ubyte * 128).from_buffer_copy(obj[0])
+        self._check(lib().rr_engine_comm_init(self._h, raw, rank, world), "rr_engine_comm_init")
 
     def fp64_peak(self) -> float:
         v = C.c_double()

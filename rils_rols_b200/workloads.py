@@ -49,6 +49,15 @@ def cfg4_data(n: int = 1_000_000, d: int = 10) -> Tuple[np.ndarray, np.ndarray]:
     return X, y
 
 
+def cfg4_truth_expr() -> B.Expr:
+    """sin(1/x0)+sin(1/x1)+sin(1/x2)+sin(1/x3)+sin(1/x4): the generating formula of cfg4_data."""
+    v = B.Expr.var
+    e = B.sin(1.0 / v(0))
+    for i in range(1, 5):
+        e = e + B.sin(1.0 / v(i))
+    return e
+
+
 def cfg5_neighbourhood() -> B.Batch:
     """The committed 4096-candidate OLS_FIT batch (tests/golden/cfg5_neighbourhood.npz)."""
     z = np.load(os.path.join(GOLDEN_DIR, "cfg5_neighbourhood.npz"))

@@ -9,7 +9,7 @@ configs, the rr_batch arrays (term bytecode as the reference's own factor select
 produced it) plus what the reference computed per candidate — QR coefficients,
 nonzero_pivots, and the fitness tuple (1-R2, RMSE, size) of the tuned tree.
 
-    python tests/golden/make_golden.py            # configs 1-3 + the d=20 neighbourhood
+    python tests/golden/make_golden.py            # configs 1-3, the d=20 neighbourhood, config 4 (10^6 rows: minutes)
     python tests/golden/make_golden.py --cfg5-n 16777216   # tune the cfg-5 base on the full 2^24 rows
 """
 from __future__ import annotations
@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import pyoracle as O  # noqa: E402
 from rils_rols_b200 import batch as B  # noqa: E402
-from rils_rols_b200.workloads import cfg5_data, cfg5_base_expr, config_data  # noqa: E402
+from rils_rols_b200.workloads import cfg4_data, cfg4_truth_expr, cfg5_data, cfg5_base_expr, config_data  # noqa: E402
 
 
 def to_batch(g) -> B.Batch:
@@ -123,11 +123,54 @@ def cfg5(R, n_tune, n_score=4096, n_cand=4096, max_term_nodes=50):
     print(f"cfg5 -> {os.path.getsize(path) / 1e3:.0f} kB")
 
 
+def cfg4(R, n=1_000_000, d=10, max_cands_first=100000, max_cands_truth=320):
+    """BASELINE config 4 (test_large.py style): 10^6 x 10 synthetic, y = sum_{i<5} sin(1/x_i),
+    NOISE-FREE - the near-perfect-fit regime of SURVEY.md 7.2-3. Two neighbourhoods scored by the unmodified
+    reference on all 10^6 rows: (ls0) the first local-search neighbourhood fit() reaches (fit_inner :799-842:
+    perturbations of const 0, best by 1-R2, tune_constants, all_candidates(local_search=true)), and (ls1) a prefix of
+    the neighbourhood of the ground truth itself, where most candidates fit to rounding level."""
+    t0 = time.time()
+    X, y = cfg4_data(n, d)
+    h = R.RefHarness(False, 0.001, 50, 12345)
+    h.set_data(X, y)
+    zero = B.Expr.const(0.0).program()
+    perts = h.all_candidates(zero[0], zero[1], False)
+    rec, g = record(h, perts, False)
+    fx = {"n": np.int64(n), "d": np.int32(d), "x_checksum": np.float64(X.sum()), "y_checksum": np.float64(y.sum())}
+    fx.update({f"pert0_{k}": v for k, v in rec.items()})
+    print(f"cfg4: {len(perts)} perturbations scored ({time.time() - t0:.1f}s)")
+    order = np.argsort(g["ref_f0"], kind="stable")
+    p = perts[int(order[0])]
+    cur = h.tune(p[0], p[1], False)
+    ls = h.all_candidates(cur["tuned_code"], cur["tuned_consts"], True)[:max_cands_first]
+    rec, g = record(h, ls, True)
+    fx.update({f"ls0_{k}": v for k, v in rec.items()})
+    fx["ls0_base_str"] = np.array(cur["tuned_str"])
+    print(f"cfg4 ls0: base {cur['tuned_str']}, {len(ls)} candidates ({time.time() - t0:.1f}s)")
+    truth = cfg4_truth_expr().program()
+    cur = h.tune(truth[0], truth[1], False)
+    print(f"cfg4 truth tuned: {cur['tuned_str']} fitness={cur['fitness']}")
+    ls = h.all_candidates(cur["tuned_code"], cur["tuned_consts"], True)
+    # every 7th tree: a spread over all generator kinds instead of the first node's candidates only
+    ls = ls[::max(1, len(ls) // max_cands_truth)][:max_cands_truth]
+    rec, g = record(h, ls, True)
+    fx.update({f"ls1_{k}": v for k, v in rec.items()})
+    fx["ls1_base_str"] = np.array(cur["tuned_str"])
+    fx["n_ls"] = np.int32(2)
+    k = np.diff(g["cand_term_begin"]) + 1
+    print(f"cfg4 ls1: {len(ls)} candidates, near-perfect (f0 < 1e-20): {(g['ref_f0'] < 1e-20).sum()}, "
+          f"rankdef {(g['ref_nonzero_pivots'] < k).sum()}, sentinels {(g['ref_size'] == 1000).sum()} ({time.time() - t0:.1f}s)")
+    path = os.path.join(HERE, "cfg4_large.npz")
+    np.savez_compressed(path, **fx)
+    print(f"cfg4 -> {os.path.getsize(path) / 1e3:.0f} kB")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg5-n", type=int, default=1 << 24)
     ap.add_argument("--skip-cfg5", action="store_true")
     ap.add_argument("--skip-small", action="store_true")
+    ap.add_argument("--skip-cfg4", action="store_true")
     args = ap.parse_args()
     R = O.load_ref()
     if R is None:
@@ -138,6 +181,8 @@ def main():
             small_config(R, name, X, y, cls, mc, 12345)
     if not args.skip_cfg5:
         cfg5(R, args.cfg5_n)
+    if not args.skip_cfg4:
+        cfg4(R)
 
 
 if __name__ == "__main__":

@@ -51,84 +51,239 @@ def fitness_arrays(batch: B.Batch, res: B.Result, sst: float, n: int, coef=None)
     return f0, f1, fs
 
 
-def design_condition(Xfm, batch: B.Batch, c: int, evaluate) -> float:
-    """2-norm condition number of the column-normalised design matrix of candidate c."""
+_COL_CACHE: dict = {}
+_COL_CACHE_ID = [None]
+
+
+def term_columns(Xfm, batch: B.Batch, c: int, evaluate):
+    """The candidate's design matrix as the reference builds it (rils_rols_cpp.cpp:477-482): one column per
+    factor, ones last. Columns of repeated terms are evaluated once per data set (a local-search
+    neighbourhood repeats 90 % of its terms)."""
+    if _COL_CACHE_ID[0] != id(Xfm):
+        _COL_CACHE.clear()
+        _COL_CACHE_ID[0] = id(Xfm)
     t0, t1 = int(batch.cand_term_begin[c]), int(batch.cand_term_begin[c + 1])
     cols = []
     for t in range(t0, t1):
         code = batch.code[batch.term_code_begin[t]:batch.term_code_begin[t + 1]]
-        cols.append(evaluate(Xfm, code, batch.consts))
+        kidx = [int(w >> 8) for w in code.tolist() if (w & 0xFF) == B.OP_CONST]
+        key = (code.tobytes(), tuple(float(batch.consts[i]).hex() for i in kidx))
+        col = _COL_CACHE.get(key)
+        if col is None:
+            col = evaluate(Xfm, code, batch.consts)
+            if len(_COL_CACHE) * Xfm.shape[1] * 8 > 2e9:
+                _COL_CACHE.clear()
+            _COL_CACHE[key] = col
+        cols.append(col)
     cols.append(np.ones(Xfm.shape[1]))
-    A = np.stack(cols, axis=1)
+    return np.stack(cols, axis=1)
+
+
+def condition_of(A) -> float:
+    """2-norm condition number of the column-normalised matrix (inf when a column is zero / non-finite).
+    Tall matrices (n > 50 000) go through the eigenvalues of the normalised Gram matrix: exact enough to
+    decide kappa <= 1e6 (kappa^2 = 1e12 is far above the 1e-16 eigenvalue resolution)."""
+    if A.shape[1] == 0:
+        return 1.0
     if not np.all(np.isfinite(A)):
         return np.inf
     nrm = np.linalg.norm(A, axis=0)
     if np.any(nrm == 0):
         return np.inf
+    if A.shape[0] > 50000:
+        An = A / nrm
+        ev = np.linalg.eigvalsh(An.T @ An)
+        return float(np.sqrt(ev[-1] / ev[0])) if ev[0] > 0 else np.inf
     s = np.linalg.svd(A / nrm, compute_uv=False)
     return float(s[0] / s[-1]) if s[-1] > 0 else np.inf
+
+
+def design_condition(Xfm, batch: B.Batch, c: int, evaluate) -> float:
+    """2-norm condition number of the column-normalised design matrix of candidate c."""
+    return condition_of(term_columns(Xfm, batch, c, evaluate))
+
+
+def ls_optimum_ssr(A, y) -> float:
+    """Smallest residual sum of squares any coefficient vector can reach (SVD least squares on the
+    column-normalised design): no correct implementation can report less, whatever it does about rank."""
+    nrm = np.linalg.norm(A, axis=0)
+    nrm[nrm == 0] = 1.0
+    sol = np.linalg.lstsq(A / nrm, y, rcond=None)[0]
+    r = y - (A / nrm) @ sol
+    return float(r @ r)
+
+
+TRANSCENDENTAL = {B.OP_SIN, B.OP_COS, B.OP_LN, B.OP_EXP, B.OP_POW}
+LOOSE = 1e-6          # stated looser bound for candidates whose reference answer is ill-conditioned
+HUGE_COEF = 1e8       # beyond this the reference kept a numerically dependent column "with garbage" (SURVEY B.6)
 
 
 def compare(batch: B.Batch, res: B.Result, ref: dict, Xfm, y, sst: float, evaluate, label: str = "",
             check_nzp: bool = True):
     """ref: dict with ref_coef, ref_nonzero_pivots, ref_f0, ref_f1, ref_size (golden or oracle).
+    check_nzp = the engine ran the reference's own column-pivoted QR (exact path): rank decisions are
+    comparable. Every candidate is asserted on, by class (counts are returned and printed by the callers):
+
+      well_posed     reference full rank, kappa <= 1e6, finite: coefficients, size, f0, f1 to 1e-9 (+ nonzero_pivots)
+      rankdef_drop   reference dropped a column (nonzero_pivots < k, moderate coefficients): the drop outcome
+                     SURVEY B.7 says must be reproduced. Exact path: same nonzero_pivots, same zero pattern,
+                     coefficients (when the kept columns are well conditioned), size and fitness to 1e-9; a
+                     different rank decision ("rank_flip") is tolerated only when the candidate contains a
+                     transcendental (libm vs libdevice differ by an ulp and the threshold is at rounding level,
+                     ColPivHouseholderQR.h:511) and then falls under the Gram-path rule. Gram path: SSR within 1e-6
+                     and never below the reference's by more than 1e-9 (the reference's SSR is the optimum of the
+                     reduced design).
+      illcond        everything else that is finite (kappa > 1e6 or a kept dependent column): the SSR can be no smaller
+                     than the least-squares optimum (SVD) beyond 1e-9 and, unless the reference itself returned
+                     garbage-level coefficients (>= 1e8: "arbitrary"), no larger than the worse of the two by 1e-6.
+      sentinel       reference (1000,1000,1000): the engine must report it too whenever a term column is itself
+                     non-finite; a NaN that only arises inside the reference's QR of a degenerate design is
+                     "sentinel_unconfirmed".
     Returns a report dict; raises AssertionError on a parity violation."""
     nc, n = batch.n_cand, Xfm.shape[1]
     f0, f1, fs = fitness_arrays(batch, res, sst, n)
     yscale = float(np.sqrt(sst / n)) if sst > 0 else 1.0
-    rep = dict(label=label, n_cand=nc, well_posed=0, ambiguous=0, sentinel=0, max_coef_err=0.0, max_fit_err=0.0,
-               loose_fail=0)
+    rep = dict(label=label, n_cand=nc, well_posed=0, rankdef_drop=0, rank_flip=0, illcond=0, arbitrary=0, ambiguous=0,
+               sentinel=0, sentinel_unconfirmed=0, snap_noise=0, max_coef_err=0.0, max_fit_err=0.0,
+               max_drop_fit_err=0.0, max_loose_err=0.0)
     ols = batch.mode == B.MODE_OLS_FIT
+    ssr_floor = 1e-12 * max(sst, 1e-300)
+
+    def check_fitness(c, tol, key):
+        for name, g, r, floor in (("f0", f0[c], ref["ref_f0"][c], 1e-12), ("f1", f1[c], ref["ref_f1"][c], 1e-12 * yscale)):
+            if np.isinf(r) or np.isinf(g):
+                assert g == r, f"{label} cand {c}: {name} {g} vs {r}"
+                continue
+            err = abs(g - r) / (abs(r) + floor / tol)  # <= tol  <=>  |g - r| <= tol*|r| + floor
+            rep[key] = max(rep[key], err * (REL / tol))
+            assert err <= tol, f"{label} cand {c}: {name} {g!r} vs {r!r} (err {err:.3e}, tol {tol:g})"
+
     for c in range(nc):
         ref_sent = ref["ref_size"][c] == 1000 and ref["ref_f0"][c] == 1000
+        if not ols:
+            if ref_sent:
+                rep["sentinel"] += 1
+                assert fs[c] == 1000 and f0[c] == 1000, f"{label} cand {c}: reference sentinel, engine {f0[c]},{f1[c]},{fs[c]}"
+                continue
+            rep["well_posed"] += 1
+            assert fs[c] == ref["ref_size"][c], f"{label} cand {c}: size {fs[c]} vs {ref['ref_size'][c]}"
+            check_fitness(c, REL, "max_fit_err")
+            continue
+
+        k = int(batch.cand_term_begin[c + 1] - batch.cand_term_begin[c]) + 1
+        sl = batch.coef_slice(c)
+        cr, cg = ref["ref_coef"][sl], res.coef[sl]
+        A = None
         if ref_sent:
             rep["sentinel"] += 1
-        well = True
-        if ols:
-            k = int(batch.cand_term_begin[c + 1] - batch.cand_term_begin[c]) + 1
-            cr = ref["ref_coef"][batch.coef_slice(c)]
-            well = (not ref_sent) and ref["ref_nonzero_pivots"][c] == min(k, n) and np.all(np.isfinite(cr))
-            if well:
-                well = design_condition(Xfm, batch, c, evaluate) <= KAPPA_MAX
-        if not well and not ref_sent:
-            rep["ambiguous"] += 1
-            # both finite: same order of magnitude of fitness is all that can be asked
-            continue
-        if ref_sent:
-            # NaN anywhere in the reference's prediction: the engine must report the sentinel too
-            # (for rank-deficient designs the NaN can hinge on rounding noise: only well-defined
-            # cases are asserted, i.e. a term itself is non-finite)
-            if not ols or (res.flags[c] & B.RES_NONFINITE):
+            A = term_columns(Xfm, batch, c, evaluate)
+            if (res.flags[c] & B.RES_NONFINITE) or not np.all(np.isfinite(A)):
+                # NaN/inf in a term: fitness() sees it whatever the solver did
                 assert fs[c] == 1000 and f0[c] == 1000, f"{label} cand {c}: reference sentinel, engine {f0[c]},{f1[c]},{fs[c]}"
             else:
+                rep["sentinel_unconfirmed"] += 1
                 rep["ambiguous"] += 1
             continue
-        rep["well_posed"] += 1
-        snap_noise = False
-        if ols:
+        full_rank = ref["ref_nonzero_pivots"][c] == min(k, n)
+        finite = bool(np.all(np.isfinite(cr)))
+        moderate = finite and float(np.max(np.abs(cr))) < HUGE_COEF
+        A = term_columns(Xfm, batch, c, evaluate)
+        kappa = condition_of(A) if (full_rank and finite) else np.inf
+        ssr_ref = float(ref["ref_f0"][c]) * sst
+        ssr_g = float(res.ssr[c])
+
+        if full_rank and finite and kappa <= KAPPA_MAX:
+            rep["well_posed"] += 1
             # a reference coefficient sitting in the rounding-noise band around a snap threshold
             # (|c| or |c-1| between 1e-14 and 1e-10; the thresholds are 1e-12, node.h:333-339) makes
             # the tree SIZE a coin flip in the reference itself: coefficients are still checked,
             # size / fitness are not
-            for v in np.concatenate([np.abs(cr), np.abs(cr[:-1] - 1.0)]):
-                if 1e-14 < v < 1e-10:
-                    snap_noise = True
-            cg = res.coef[batch.coef_slice(c)]
+            snap_noise = any(1e-14 < v < 1e-10 for v in np.concatenate([np.abs(cr), np.abs(cr[:-1] - 1.0)]))
             scale = max(float(np.max(np.abs(cr))), 1e-300)
             err = float(np.max(np.abs(cg - cr))) / scale
             rep["max_coef_err"] = max(rep["max_coef_err"], err)
             assert err <= REL, f"{label} cand {c}: coefficient error {err:.3e} (gpu {cg}, ref {cr})"
             if check_nzp:
                 assert res.nonzero_pivots[c] == ref["ref_nonzero_pivots"][c], f"{label} cand {c}: nonzero_pivots"
-        if snap_noise:
-            rep["snap_noise"] = rep.get("snap_noise", 0) + 1
-            continue
-        assert fs[c] == ref["ref_size"][c], f"{label} cand {c}: size {fs[c]} vs {ref['ref_size'][c]}"
-        for name, g, r, floor in (("f0", f0[c], ref["ref_f0"][c], 1e-12), ("f1", f1[c], ref["ref_f1"][c], 1e-12 * yscale)):
-            if np.isinf(r) or np.isinf(g):
-                assert g == r, f"{label} cand {c}: {name} {g} vs {r}"
+            if snap_noise:
+                rep["snap_noise"] += 1
                 continue
-            err = abs(g - r) / (abs(r) + floor / REL)  # <= REL  <=>  |g - r| <= REL*|r| + floor
-            rep["max_fit_err"] = max(rep["max_fit_err"], err)
-            assert err <= REL, f"{label} cand {c}: {name} {g!r} vs {r!r} (err {err:.3e})"
+            assert fs[c] == ref["ref_size"][c], f"{label} cand {c}: size {fs[c]} vs {ref['ref_size'][c]}"
+            check_fitness(c, REL, "max_fit_err")
+            continue
+
+        rep["ambiguous"] += 1
+        assert np.isfinite(ssr_g) or np.isnan(ssr_g) or np.isinf(ssr_g)
+        if (not full_rank) and moderate:
+            rep["rankdef_drop"] += 1
+            same_rank = check_nzp and res.nonzero_pivots[c] == ref["ref_nonzero_pivots"][c] and \
+                np.array_equal(cg == 0.0, cr == 0.0)
+            if check_nzp and not same_rank:
+                t0, t1 = int(batch.cand_term_begin[c]), int(batch.cand_term_begin[c + 1])
+                ops = set((batch.code[batch.term_code_begin[t0]:batch.term_code_begin[t1]] & 0xFF).tolist())
+                assert ops & TRANSCENDENTAL, \
+                    f"{label} cand {c}: arithmetic-only candidate, rank decision differs: nzp {res.nonzero_pivots[c]} vs " \
+                    f"{ref['ref_nonzero_pivots'][c]}, gpu {cg}, ref {cr}"
+                rep["rank_flip"] += 1
+            if same_rank:
+                kept = cr != 0.0
+                if condition_of(A[:, kept]) <= KAPPA_MAX:
+                    scale = max(float(np.max(np.abs(cr))), 1e-300)
+                    err = float(np.max(np.abs(cg - cr))) / scale
+                    rep["max_coef_err"] = max(rep["max_coef_err"], err)
+                    assert err <= REL, f"{label} cand {c}: rank-deficient, coefficient error {err:.3e} (gpu {cg}, ref {cr})"
+                    if not any(1e-14 < v < 1e-10 for v in np.concatenate([np.abs(cr[kept]), np.abs(cr[:-1] - 1.0)])):
+                        assert fs[c] == ref["ref_size"][c], f"{label} cand {c}: size {fs[c]} vs {ref['ref_size'][c]}"
+                        check_fitness(c, REL, "max_drop_fit_err")
+                    else:
+                        rep["snap_noise"] += 1
+                    continue
+            # Gram path (or a tolerated flip / ill-conditioned remainder): the reference's SSR is the optimum of the
+            # reduced design
+            assert np.isfinite(ssr_g), f"{label} cand {c}: reference finite ({ssr_ref}), engine {ssr_g}"
+            assert ssr_g >= ssr_ref * (1 - REL) - ssr_floor, f"{label} cand {c}: ssr {ssr_g!r} below the reference's {ssr_ref!r}"
+            err = (ssr_g - ssr_ref) / (abs(ssr_ref) + ssr_floor / LOOSE)
+            rep["max_loose_err"] = max(rep["max_loose_err"], err)
+            assert err <= LOOSE, f"{label} cand {c}: rank-deficient, ssr {ssr_g!r} vs {ssr_ref!r} (err {err:.3e})"
+            continue
+
+        # ill-conditioned / kept-with-garbage: bounded by the least-squares optimum from below
+        rep["illcond"] += 1
+        if not np.all(np.isfinite(A)):
+            continue  # cannot happen for a finite reference fitness; nothing to compare
+        ssr_opt = min(ls_optimum_ssr(A, y), ssr_ref if np.isfinite(ssr_ref) else np.inf)
+        if not np.isfinite(ssr_g):
+            # the reference got through with finite numbers, the engine did not: only legitimate at garbage level
+            assert not moderate, f"{label} cand {c}: reference finite ({ssr_ref}, coef {cr}), engine {ssr_g}"
+            rep["arbitrary"] += 1
+            continue
+        assert ssr_g >= ssr_opt * (1 - REL) - ssr_floor - 1e-9 * ssr_opt, \
+            f"{label} cand {c}: ssr {ssr_g!r} below the least-squares optimum {ssr_opt!r}"
+        worst = max(ssr_ref if np.isfinite(ssr_ref) else 0.0, ssr_opt)
+        err = (ssr_g - worst) / (abs(worst) + ssr_floor / LOOSE)
+        if err > LOOSE:
+            assert not moderate, f"{label} cand {c}: ill-conditioned, ssr {ssr_g!r} vs reference {ssr_ref!r} / optimum {ssr_opt!r}"
+            rep["arbitrary"] += 1
+        else:
+            rep["max_loose_err"] = max(rep["max_loose_err"], err)
     return rep
+
+
+def summary(reports) -> dict:
+    """Per-class totals over several reports (what the tests print and profiles/r2_parity_classes.txt records)."""
+    keys = ("n_cand", "well_posed", "rankdef_drop", "rank_flip", "illcond", "arbitrary", "sentinel", "sentinel_unconfirmed",
+            "snap_noise")
+    out = {k: int(sum(r.get(k, 0) for r in reports)) for k in keys}
+    for k in ("max_coef_err", "max_fit_err", "max_drop_fit_err", "max_loose_err"):
+        out[k] = float(max([r.get(k, 0.0) for r in reports] + [0.0]))
+    return out
+
+
+def record(label: str, data: dict) -> None:
+    """Appends one JSON line to $RR_PARITY_LOG (the per-class counts committed under profiles/)."""
+    import json
+
+    path = os.environ.get("RR_PARITY_LOG")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps(dict(label=label, **data)) + "\n")

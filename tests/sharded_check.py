@@ -1,5 +1,6 @@
 """Run under torchrun (one rank per GPU): sample-sharded engine vs the unsharded engine on rank 0.
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/sharded_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/sharded_check.py [hook]
+Default: NCCL inside the engine (rr_engine_comm_init); `hook`: the Python all-reduce callback.
 Prints SHARDED_OK on rank 0 when every candidate agrees to 1e-9."""
 import os
 import sys
@@ -26,9 +27,12 @@ def main():
     batch = workloads.cfg5_neighbourhood().subset(range(0, 4096, 8))
     lo, hi = rank * n // world, (rank + 1) * n // world
     eng = Engine(np.ascontiguousarray(X[lo:hi]), np.ascontiguousarray(y[lo:hi]), device=local)
-    eng.set_allreduce_torch()
+    if len(sys.argv) > 1 and sys.argv[1] == "hook":
+        eng.set_allreduce_torch()
+    else:
+        eng.comm_init_torch()
     info = eng.info()
-    assert info.n == hi - lo and info.n_total == n
+    assert info.n == hi - lo and info.n_total == n and info.world == world
     res = eng.score(batch)
     ev = B.Batch.from_exprs(B.MODE_EVAL_ONLY, [[B.sin(B.Expr.var(0)) * B.Expr.var(3)], [B.Expr.const(0.0)]])
     res_ev = eng.score(ev)

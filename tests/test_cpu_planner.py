@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     L = E.lib()
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/rr_b200.h but not exported"
-    assert L.rr_abi_version() == 1
+    assert L.rr_abi_version() == E.ABI_VERSION == 2 and set(names) == set(E.EXPORTS)
 
 
 def test_no_cpu_fallback():
@@ -38,6 +38,28 @@ def test_no_cpu_fallback():
     with pytest.raises(E.EngineError) as ei:
         E.Engine(np.ones((8, 2)), np.ones(8))
     assert "no CUDA device" in str(ei.value) or "CPU fallback" in str(ei.value)
+    with pytest.raises(E.EngineError) as ei:
+        E.Engine.sharded(np.ones((4096, 2)), np.ones(4096), n_gpus=2)
+    assert "no CUDA device" in str(ei.value) or "CPU fallback" in str(ei.value)
+
+
+def test_malformed_batches_are_rejected_on_the_host():
+    """negative / decreasing offsets and offsets beyond the code length must come back as an error string
+    from the planner (the C ABI turns it into RR_ERR_INVALID), never as an exception or an out-of-bounds read."""
+    def plan_error(ctb, tcb, code, consts):
+        b = B.Batch(B.MODE_OLS_FIT, np.asarray(ctb), np.asarray(tcb), np.asarray(code, dtype=np.uint32), np.asarray(consts, dtype=np.float64))
+        try:
+            EMU.Plan(b, 2, EMU.KIND_GRAM, tile_cols=20)
+            return ""
+        except ValueError as ex:
+            return str(ex) or "error"
+
+    assert plan_error([0, 1], [0, 1], [B.ins(B.OP_VAR, 0)], []) == ""
+    for msg in (plan_error([0, -1], [0, 1], [B.ins(B.OP_VAR, 0)], []),          # negative term count
+                plan_error([0, 2, 1], [0, 1, 2], [B.ins(B.OP_VAR, 0)] * 2, []),   # decreasing candidate offsets
+                plan_error([0, 1], [0, 5], [B.ins(B.OP_VAR, 0)], []),             # term beyond the code array (n_code = 1)
+                plan_error([0, 1], [0, 1], [B.ins(B.OP_CONST, 3)], [1.0])):       # constant index out of range
+        assert msg, msg
 
 
 def gram_from_dots(plan, dots, batch, c, n):
