@@ -31,6 +31,7 @@
 #include "rr_plan.h"
 #include "rr_solve.cuh"
 #include "rr_sweep.cuh"
+#include "rr_sweep_g8.cuh"
 
 namespace {
 
@@ -495,8 +496,16 @@ std::vector<rr_engine *> shards_of(rr_engine *e)
 
 // One shard, one plan: upload the plan, zero the accumulators, launch the interpreter on s->stream, reduce the block
 // rows into (s->*dots) + dots_off. No synchronisation. `e` (the leader) only receives the error text.
+// tile columns a G8 plan may use (rr_sweep_g8.cuh: padded columns behind the staging rows, two blocks per SM)
+int g8_tile_cols()
+{
+    const size_t per_block = kSmemPerSM / 2 - kSmemReserved - rr::kG8StaticBytes;
+    return (int)((per_block - rr::kG8StageBytes) / rr::kG8ColBytes);
+}
+
 int launch_shard(rr_engine *e, rr_engine *s, const rr::SweepPlan &P, const std::vector<RRIns> &ins_padded, const SweepCfg &cfg,
-                 const XView &view, DotsMember dots, bool dd, double *stg, int64_t ld_stg, int set, size_t dots_off)
+                 const XView &view, DotsMember dots, bool dd, double *stg, int64_t ld_stg, int set, size_t dots_off, bool g8 = false,
+                 bool mark_begin = true)
 {
     DevBuf &d_ins = set ? s->d_ins2 : s->d_ins, &d_chunks = set ? s->d_chunks2 : s->d_chunks;
     DevBuf &d_cols = set ? s->d_cols2 : s->d_cols, &d_acc = set ? s->d_acc2 : s->d_acc;
@@ -505,15 +514,28 @@ int launch_shard(rr_engine *e, rr_engine *s, const rr::SweepPlan &P, const std::
     const int T = cfg.T();
     const int NW = cfg.TH / 32;
     const int n_tiles = (int)((view.n + T - 1) / T);
-    const size_t smem = (size_t)std::max(P.max_tile_cols, 1) * T * 8 + rr::sweep_ring_smem(NW, cfg.slack);
-    if (smem > cfg.dyn_smem_budget() + rr::sweep_ring_smem(NW, cfg.slack)) return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
+    const size_t tile_bytes = (size_t)std::max(P.max_tile_cols, 1) * T * 8;
+    if (g8 ? P.max_tile_cols > g8_tile_cols() : tile_bytes > cfg.dyn_smem_budget())
+        return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
+    // two tile buffers when they fit: the next tile's columns are fetched while this one is interpreted (what an
+    // HBM-bound sweep - one small program over many rows - needs; the big neighbourhoods fill the tile and do not care)
+    const bool tile_dbuf = !g8 && 2 * tile_bytes <= cfg.dyn_smem_budget() && env_int("RR_B200_TILE_DBUF", 1) != 0;
+    const size_t smem = g8 ? rr::g8_dyn_smem(std::max(P.max_tile_cols, 1)) : tile_bytes * (tile_dbuf ? 2 : 1) + rr::sweep_ring_smem(NW, cfg.slack);
     bool special = dd;
     for (const RRIns &x : P.ins)
         if (RR_OP(x.w0) == RI_CLSMET) { special = true; break; }
-    SweepKernel kern = sweep_kernel_for(cfg, special);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemPerBlockMax - rr::sweep_static_smem())));
+    SweepKernel kern = g8 ? (SweepKernel)rr::rr_sweep_g8_kernel : sweep_kernel_for(cfg, special);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            g8 ? (int)rr::g8_dyn_smem(g8_tile_cols()) : (int)(kSmemPerBlockMax - rr::sweep_static_smem())));
     const int n_chunks = (int)P.chunks.size();
-    int gx = sweep_gx(s, cfg, special, smem, n_chunks, std::max(1, n_tiles));
+    int gx;
+    if (g8) {
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cfg.TH, smem);
+        gx = std::min(std::max(1, s->sm_count * std::max(1, occ) / std::max(1, n_chunks)), std::max(1, n_tiles));
+    } else {
+        gx = sweep_gx(s, cfg, special, smem, n_chunks, std::max(1, n_tiles));
+    }
     const int64_t stride = round_up(std::max(P.n_dots, 1), 32) + 32;
     // keep the accumulator rows within a sane budget
     const size_t row_budget = (size_t)env_double("RR_B200_ACC_BYTES", 6e9);
@@ -551,7 +573,9 @@ int launch_shard(rr_engine *e, rr_engine *s, const rr::SweepPlan &P, const std::
     a.ld_stg = ld_stg;
     a.n_tiles = n_tiles;
     a.dd_ring = env_int("RR_B200_DD_RING", 1);
-    CU(cudaEventRecord(ev0, s->stream));
+    a.tile_dbuf = tile_dbuf ? 1 : 0;
+    a.tile_buf_doubles = (int64_t)(tile_bytes / 8);
+    if (mark_begin) CU(cudaEventRecord(ev0, s->stream));
     kern<<<dim3(gx, n_chunks), cfg.TH, smem, s->stream>>>(a);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ev1, s->stream));
@@ -640,7 +664,7 @@ int reduce_over_ranks(rr_engine *e, DotsMember dots, size_t off, size_t count, b
 // dots + dots_off (the caller has sized `dots` for all pieces: growing it here would drop the earlier ones),
 // and with sync = false the call returns right after the launches (finish_sweep reads the time later).
 int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DotsMember dots, bool dd, double *stg, int64_t ld_stg,
-              int set = 0, size_t dots_off = 0, bool sync = true)
+              int set = 0, size_t dots_off = 0, bool sync = true, bool g8 = false, bool reduce = true, bool mark_begin = true)
 {
     if (P.chunks.empty()) return RR_OK;
     // the kernel streams whole windows of kInsWindow instructions: pad the tail with ENDs
@@ -651,11 +675,11 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DotsMem
     int rc = RR_OK;
     for (rr_engine *s : shards_of(e)) {
         const XView view{s->X.as<double>(), s->ld, s->n};
-        if ((rc = launch_shard(e, s, P, ins, cfg, view, dots, dd, stg, ld_stg, set, dots_off))) break;
+        if ((rc = launch_shard(e, s, P, ins, cfg, view, dots, dd, stg, ld_stg, set, dots_off, g8, mark_begin))) break;
     }
     if (e->grouped()) cudaSetDevice(e->device);
     if (rc) return rc;
-    if (P.n_dots > 0 && (rc = reduce_over_ranks(e, dots, dots_off, (size_t)P.n_dots, dd))) return rc;
+    if (reduce && P.n_dots > 0 && (rc = reduce_over_ranks(e, dots, dots_off, (size_t)P.n_dots, dd))) return rc;
     e->stats.distinct_dots += P.n_dot_ins;
     e->stats.w_shared += P.w_issued;
     if (!sync) return RR_OK;
@@ -1137,75 +1161,113 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     if (rc) return rc;
 
     // pass 1: Gram / A^T yc / column sums, shared across candidates.
-    // A large neighbourhood on a large data set is planned in two halves, the second on a helper thread: its
-    // planning overlaps the first half's planning, launch and sweep (planning is host work, ~1 us per
-    // candidate; with the rows sharded over several GPUs it is otherwise a visible part of the step). The halves share nothing but the
-    // base solution's terms, which each half evaluates and reduces once (a few dozen instructions).
-    rr::SweepPlan P1;
-    std::vector<int32_t> tab, tab_begin;
+    // The neighbourhood is planned in PIECES - contiguous runs of candidates - on helper threads, and every piece is
+    // launched as soon as its plan exists: planning (host work, ~1 us per candidate) hides behind the sweeps of the
+    // pieces before it instead of preceding the whole step, which is what bounds a step once the rows are sharded
+    // over several GPUs. Pieces share nothing but the base solution's terms, which each piece evaluates and pins
+    // once (a few dozen instructions). On the 4-samples-per-thread shape the pieces are G8 plans (reductions by
+    // DMMA, rr_sweep_g8.cuh); candidates with more terms than there are pins form one classic piece of their own.
+    // All pieces write into one dot vector, which is summed over shards / ranks ONCE behind the last piece.
+    struct Piece {
+        std::vector<int32_t> list;
+        bool g8 = false;
+        rr::SweepPlan P;
+        std::vector<int32_t> tab, tab_begin;
+        std::string err;
+        size_t off = 0;
+    };
+    std::vector<Piece> pieces;
+    const bool big_shape = S.S == 4 && S.TH == 128 && lim.target_chunks == 1;
+    const bool use_g8 = big_shape && env_int("RR_B200_G8", 1) != 0 && e->d + 3 <= g8_tile_cols();
+    {
+        const bool pipelined = env_int("RR_B200_PIPELINE", 1) != 0 && nc >= 1024 && big_shape;
+        const int want = pipelined ? std::max(1, env_int("RR_B200_PIECES", 4)) : 1;
+        std::vector<int32_t> main_list, wide;
+        for (int c = 0; c < nc; ++c) (use_g8 && bp.k_of(c) - 1 > RR_NPIN ? wide : main_list).push_back(c);
+        const int np = (int)std::min<size_t>((size_t)want, std::max<size_t>(1, main_list.size() / 256));
+        for (int i = 0; i < np && !main_list.empty(); ++i) {
+            Piece pc;
+            pc.g8 = use_g8;
+            pc.list.assign(main_list.begin() + main_list.size() * i / np, main_list.begin() + main_list.size() * (i + 1) / np);
+            pieces.push_back(std::move(pc));
+        }
+        if (!wide.empty()) {
+            Piece pc;
+            pc.list = std::move(wide);
+            pieces.push_back(std::move(pc));
+        }
+    }
+    rr::PlanLimits lim_g8 = lim;
+    lim_g8.tile_cols = g8_tile_cols();
+    lim_g8.g8 = true;
+    lim_g8.mdot_rows = false;
     std::string err;
-    const bool pipelined = env_int("RR_B200_PIPELINE", 1) != 0 && nc >= 1024 && S.S == 4 && lim.target_chunks == 1;
-    if (!pipelined) {
-        err = bp.plan_gram(lim, cols, nullptr, false, P1, tab, tab_begin);
-        if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
-        phase("plan gram");
-        rc = run_sweep(e, P1, S, &rr_engine::d_dots, false, nullptr, 0);
-        if (rc) return rc;
-        phase("sweep gram");
-    } else {
-        // the reduced dots of both halves live in one vector: size it before the first launch
+    auto plan_piece = [&](Piece &pc) {
+        pc.err = pc.g8 ? bp.plan_gram_g8(lim_g8, cols, &pc.list, pc.P, pc.tab, pc.tab_begin)
+                       : bp.plan_gram(lim, cols, &pc.list, false, pc.P, pc.tab, pc.tab_begin);
+    };
+    std::vector<int32_t> tab, tab_begin;
+    {
+        // the reduced dots of all pieces live in one vector: size it before the first launch
         size_t tab_total = 0;
         for (int c = 0; c < nc; ++c) {
             const size_t m = (size_t)bp.k_of(c) - 1;
             tab_total += m * (m + 1) / 2 + 2 * m;
         }
-        CU(e->d_dots.ensure((tab_total + 256) * 8));
-        const int half = nc / 2;
-        std::vector<int32_t> la(half), lb(nc - half);
-        for (int c = 0; c < half; ++c) la[c] = c;
-        for (int c = half; c < nc; ++c) lb[c - half] = c;
-        // the second half is planned on a helper thread (plan_gram only reads the analysed batch): it overlaps
-        // the first half's planning and launch, and - when an all-reduce hook blocks this thread until the
-        // first sweep is done - the first sweep as well
-        rr::SweepPlan P2;
-        std::vector<int32_t> tab2, tab2_begin;
-        std::string err2;
-        auto plan_second = [&]() { err2 = bp.plan_gram(lim, cols, &lb, false, P2, tab2, tab2_begin); };
-        std::thread planner2;
-        struct Joiner {  // whatever path leaves this scope, the helper is joined first (it writes to the locals above)
-            std::thread &t;
+        const size_t dots_cap = tab_total + 64 * pieces.size() + 256;
+        for (rr_engine *s : shards_of(e)) {
+            CU(cudaSetDevice(s->device));
+            CU(s->d_dots.ensure(dots_cap * 8));
+        }
+        CU(cudaSetDevice(e->device));
+        std::vector<std::thread> helpers(pieces.size());
+        struct Joiner {  // whatever path leaves this scope, the helpers are joined first (they write into `pieces`)
+            std::vector<std::thread> &t;
             ~Joiner()
             {
-                if (t.joinable()) t.join();
+                for (std::thread &x : t)
+                    if (x.joinable()) x.join();
             }
-        } joiner{planner2};
-        bool threaded = true;
-        try {
-            planner2 = std::thread(plan_second);
-        } catch (...) {
-            threaded = false;  // no thread to be had: plan the second half here, after the first launch
+        } joiner{helpers};
+        std::vector<char> threaded(pieces.size(), 0);
+        for (size_t i = 1; i < pieces.size(); ++i) {
+            try {
+                helpers[i] = std::thread(plan_piece, std::ref(pieces[i]));
+                threaded[i] = 1;
+            } catch (...) {  // no thread to be had: that piece is planned here, when its turn comes
+            }
         }
-        err = bp.plan_gram(lim, cols, &la, false, P1, tab, tab_begin);
-        if (!err.empty()) {
-            if (threaded) planner2.join();
-            return e->fail(RR_ERR_INVALID, err);
+        size_t off = 0;
+        for (size_t i = 0; i < pieces.size(); ++i) {
+            Piece &pc = pieces[i];
+            if (threaded[i]) helpers[i].join();
+            else plan_piece(pc);
+            if (!pc.err.empty()) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, pc.err); }
+            pc.off = off;
+            if (off + (size_t)pc.P.n_dots > dots_cap) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, "internal: dot vector too small"); }
+            rc = run_sweep(e, pc.P, S, &rr_engine::d_dots, false, nullptr, 0, (int)(i & 1), off, false, pc.g8, false, i == 0);
+            if (rc) { cudaStreamSynchronize(e->stream); return rc; }
+            off += (size_t)round_up(std::max(pc.P.n_dots, 1), 32);
         }
-        rc = run_sweep(e, P1, S, &rr_engine::d_dots, false, nullptr, 0, 0, 0, false);
-        if (threaded) planner2.join();
-        else if (!rc) plan_second();
-        if (rc) { cudaStreamSynchronize(e->stream); return rc; }
-        if (!err2.empty()) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, err2); }
-        const size_t off2 = (size_t)round_up(std::max(P1.n_dots, 1), 32);
-        if (off2 + (size_t)P2.n_dots > tab_total + 256) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, "internal: dot vector too small"); }
-        rc = run_sweep(e, P2, S, &rr_engine::d_dots, false, nullptr, 0, 1, off2, false);
-        if (rc) { cudaStreamSynchronize(e->stream); return rc; }
-        const int32_t t0 = (int32_t)tab.size();
-        for (int32_t id : tab2) tab.push_back(id + (int32_t)off2);
-        for (size_t i = 1; i < tab2_begin.size(); ++i) tab_begin.push_back(tab2_begin[i] + t0);
+        if ((rc = reduce_over_ranks(e, &rr_engine::d_dots, 0, off, false))) { cudaStreamSynchronize(e->stream); return rc; }
+        // per-candidate tables in candidate order
+        std::vector<std::pair<int32_t, int32_t>> where(nc);
+        for (size_t i = 0; i < pieces.size(); ++i)
+            for (size_t j = 0; j < pieces[i].list.size(); ++j) where[pieces[i].list[j]] = {(int32_t)i, (int32_t)j};
+        tab_begin.assign(1, 0);
+        for (int c = 0; c < nc; ++c) {
+            const Piece &pc = pieces[where[c].first];
+            for (int32_t k = pc.tab_begin[where[c].second]; k < pc.tab_begin[where[c].second + 1]; ++k) tab.push_back(pc.tab[k] + (int32_t)pc.off);
+            tab_begin.push_back((int32_t)tab.size());
+        }
         CU(cudaStreamSynchronize(e->stream));
-        finish_sweep(e, 0);
-        finish_sweep(e, 1);
-        phase("plan + sweep gram (two halves)");
+        // the pieces' sweeps as one span: from the first launch (event 2 of the first piece) to the end of the last
+        {
+            float ms = 0.f;
+            const int last = (int)((pieces.size() - 1) & 1);
+            if (cudaEventElapsedTime(&ms, e->ev[2], e->ev[last ? 5 : 3]) == cudaSuccess) e->sweep_ms_accum += ms;
+        }
+        phase("plan + sweep gram (pieces)");
     }
 
     // per-candidate solve

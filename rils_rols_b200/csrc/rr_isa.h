@@ -66,6 +66,16 @@ enum RRInsOp : uint32_t {
     // aux bits 16-19 = 1 + j: afterwards pin[j] = t (the planner's "PIN j; MDOT" pair in one dispatch;
     // j is never in the mask).
     RI_MDOT,
+    // ---- G8 plans (Gram reductions on the FP64 tensor-core path, rr_sweep_g8.cuh) ----
+    // Up to 8 freshly evaluated terms sit in tile slots ("rows"); ONE instruction reduces all of them against the 8
+    // pins with DMMA.8x8x4 (a warp-level 8 terms x 8 pins x 4 samples product-accumulate per instruction: the
+    // accumulator fragment IS the warp total, nothing is transposed) plus each row's t.t and sum(t).
+    // w0 = RI_GRAM8 | n_rows << 8; w1, lo32(imm), hi32(imm) = 80 "wanted" bits, bit 10 g + o of row g: o = 0..7 pin o,
+    // 8 = t.t, 9 = sum(t); output ids are consecutive from the chunk's running count in bit order. A data slot
+    // (RI_NOP, aux RR_GRAM_COLS) follows: bytes 4..11 = the tile column of each row (unused rows repeat row 0).
+    RI_GRAM8,
+    // pin j (aux = j) <- engine column w1 read from global memory, as a reduction partner only (B fragment)
+    RI_PINBG,
     // double-double reductions (escalation plans): same encoding as RI_MDOT, each output accumulated in
     // double-double and taking two ids (hi, lo)
     RI_MDOTDD,
@@ -99,7 +109,10 @@ enum RRInsOp : uint32_t {
     RI_LDPMUL_M0,                             // t = reg[j] * tile[w1]   (LDP j; MUL_M)
     RI_LDPDIV_M0 = RI_LDPMUL_M0 + RR_NREG,    // t = reg[j] / tile[w1]   (LDP j; DIV_M)
     RI_LDMDIVP0 = RI_LDPDIV_M0 + RR_NREG,     // t = tile[w1] / reg[j]   (LOAD_M; USEP j; DIV_M)
-    RI_LAST_M = RI_LDMDIVP0 + RR_NREG - 1,
+    // G8 plans: pin j <- tile[w1], both as an operand register (like RI_PIN) and as a reduction partner (the lanes that
+    // own pin j in the DMMA B fragment reload their 32 samples from the column)
+    RI_PINB0 = RI_LDMDIVP0 + RR_NREG,
+    RI_LAST_M = RI_PINB0 + RR_NPIN - 1,
     RI_OPCOUNT = RI_LAST_M + 1
 };
 
@@ -120,7 +133,12 @@ enum : uint32_t {
 // skips the slot; every other interpreter executes the slot as the NOP it is and derives the rows from
 // its running count (the two agree by construction; tests/isa_emu.py checks it).
 #define RR_MDOT_ROWS 1u
+#define RR_GRAM_COLS 2u
 #define RR_THEN_MDOT 0x8000u
+// G8 plans never hold an RI_MDOT; there the same bit means "X; ST c": the handler of X stores t to tile column c
+// (bits 16-23 of w0) before it dispatches. Same set of carriers (rr_md_fusable).
+#define RR_THEN_ST 0x8000u
+#define RR_THEN_ST_COL(w0) (((w0) >> 16) & 0xffu)
 #ifdef __CUDACC__
 #define RR_HD __host__ __device__
 #else
@@ -130,7 +148,7 @@ RR_HD static inline bool rr_md_fusable(uint32_t op)
 {
     return op == RI_MUL_M || op == RI_DIV_M || op == RI_RDIV_M || op == RI_DIV_C || op == RI_RDIV_C ||
            (op >= RI_MULP0 && op < RI_FIRST_M) || op == RI_CMUL_M || op == RI_CDIV_M || op == RI_MUL_MM ||
-           (op >= RI_LDPMUL_M0 && op <= RI_LAST_M);
+           (op >= RI_LDPMUL_M0 && op < RI_PINB0);
 }
 #define RR_W0(op, aux) ((uint32_t)(op) | ((uint32_t)(aux) << 8))
 #define RR_OP(w0) ((w0) & 0xffu)

@@ -417,6 +417,16 @@ struct BatchPlanner::Chunk {
     int32_t cur_term = -1;  // distinct term being generated (next-use horizon of the cache)
     uint64_t clock = 1, epoch = 1;
     std::string err;
+    // G8 plans (rr_isa.h RI_GRAM8): fresh terms live in tile slots and are reduced eight at a time against the pins
+    bool g8 = false;
+    struct GRow {
+        uint32_t col;      // pre-patch location: slot index or STAGED | index
+        uint32_t want;     // bits 0-7 pins, 8 self, 9 one
+        bool free_after;   // the slot is a temporary of this row: released by the flush
+    };
+    std::vector<GRow> rows;          // the open group
+    std::vector<char> slot_rowheld;  // slot -> an open row reads it
+    uint64_t n_gram_groups = 0, n_gram_rows = 0;
 
     Chunk(const BatchPlanner &bp_, SweepPlan &P_, const PlanLimits &lim_, const std::vector<int32_t> &cols, int32_t pins)
         : bp(bp_), P(P_), lim(lim_)
@@ -462,6 +472,11 @@ struct BatchPlanner::Chunk {
     uint32_t reserve_pin_global(int32_t gcol)
     {
         if (n_pins < 1) { err = "internal: no pin to reserve"; return PINREF; }
+        if (g8) {
+            emit(RR_W0(RI_PINBG, 0), (uint32_t)gcol, 0.0, 0);
+            pin_term[0] = PIN_RESERVED;
+            return PINREF | 0u;
+        }
         emit(RI_LDG, (uint32_t)gcol, 0.0, 0);
         emit(RI_PIN0, 0, 0.0, 0);
         pin_term[0] = PIN_RESERVED;
@@ -486,14 +501,35 @@ struct BatchPlanner::Chunk {
             slot_term.push_back(-1);
             slot_stamp.push_back(0);
             slot_pin.push_back(0);
+            slot_rowheld.push_back(0);
         }
         if (s < 0) {
-            uint64_t best = ~0ull;
-            for (size_t i = 0; i < slot_term.size(); ++i)
-                if (slot_term[i] >= 0 && slot_pin[i] != epoch && slot_stamp[i] < best) {
-                    best = slot_stamp[i];
-                    s = (int32_t)i;
+            auto victim = [&]() {
+                int32_t v = -1;
+                uint64_t best = ~0ull;
+                for (size_t i = 0; i < slot_term.size(); ++i)
+                    if (slot_term[i] >= 0 && slot_pin[i] != epoch && !slot_rowheld[i] && slot_stamp[i] < best) {
+                        best = slot_stamp[i];
+                        v = (int32_t)i;
+                    }
+                return v;
+            };
+            s = victim();
+            if (s < 0 && g8 && !rows.empty()) {
+                // every slot is read by a row of the open group (or holds an operand of this unit): reduce the
+                // group now, which releases its temporaries
+                flush_rows();
+                for (size_t i = 0; i < slot_term.size() && s < 0; ++i)
+                    if (slot_term[i] == -1) s = (int32_t)i;
+                if (s < 0) s = victim();
+                if (s >= 0 && slot_term[s] == -1) {
+                    slot_term[s] = owner;
+                    slot_stamp[s] = clock++;
+                    slot_pin[s] = epoch;
+                    if (owner >= 0) term_loc[owner] = (uint32_t)s;
+                    return s;
                 }
+            }
             if (s < 0) { err = "tile slots exhausted"; return 0; }
             term_loc.erase(slot_term[s]);
         }
@@ -512,6 +548,7 @@ struct BatchPlanner::Chunk {
     // unit does not hold, else a tile slot
     uint32_t alloc_loc(int32_t owner)
     {
+        if (g8) return (uint32_t)alloc_slot(owner);  // pins are filled explicitly (pin_partner): they are reduction partners
         int j = -1;
         for (int i = 0; i < n_pins; ++i)
             if (pin_term[i] == -1) { j = i; break; }
@@ -804,6 +841,138 @@ struct BatchPlanner::Chunk {
                 P.n_dot_ins += 1;
             }
     }
+    // ---- G8 ------------------------------------------------------------------------------------------
+    // reduce the open group: one RI_GRAM8 + its column slot
+    void flush_rows()
+    {
+        if (rows.empty()) return;
+        uint64_t lo = 0, hi = 0;  // 80 wanted bits
+        int n_want = 0;
+        uint8_t cols8[8];
+        for (size_t g = 0; g < 8; ++g) {
+            const GRow &r = rows[g < rows.size() ? g : 0];
+            // byte encoding of a pre-patch location: bit 7 = staged column, low bits = index (patched in close())
+            cols8[g] = (uint8_t)((r.col & STAGED) ? (0x80u | (r.col & 0x7fu)) : (r.col & 0x7fu));
+            if (g >= rows.size()) continue;
+            for (int o = 0; o < 10; ++o)
+                if ((r.want >> o) & 1u) {
+                    const int bit = (int)g * 10 + o;
+                    if (bit < 64) lo |= 1ull << bit;
+                    else hi |= 1ull << (bit - 64);
+                    ++n_want;
+                }
+        }
+        RRIns gi;
+        gi.w0 = RR_W0(RI_GRAM8, (uint32_t)rows.size());
+        gi.w1 = (uint32_t)(lo & 0xffffffffu);
+        const uint64_t immbits = (lo >> 32) | (hi << 32);
+        std::memcpy(&gi.imm, &immbits, 8);
+        P.ins.push_back(gi);
+        P.w_issued += n_want;
+        RRIns d;
+        std::memset(&d, 0, sizeof(d));
+        d.w0 = RR_W0(RI_NOP, RR_GRAM_COLS);
+        std::memcpy(&d.w1, cols8, 4);
+        std::memcpy(&d.imm, cols8 + 4, 4);
+        P.ins.push_back(d);
+        for (const GRow &r : rows)
+            if (!(r.col & STAGED)) {
+                slot_rowheld[r.col] = 0;
+                if (r.free_after) free_slot((int32_t)r.col);
+            }
+        n_gram_groups++;
+        n_gram_rows += rows.size();
+        rows.clear();
+    }
+    // term v becomes (or already is) a pin: returns j. Changing a pin first reduces the open group.
+    int pin_partner(int32_t v)
+    {
+        auto it = term_loc.find(v);
+        if (it != term_loc.end() && (it->second & PINREF)) {
+            touch(it->second);
+            return (int)(it->second & 0xff);
+        }
+        int j = -1;
+        for (int i = 0; i < n_pins; ++i)
+            if (pin_term[i] == -1) { j = i; break; }
+        if (j < 0) {
+            uint64_t best = ~0ull;
+            for (int i = 0; i < n_pins; ++i)
+                if (pin_term[i] >= 0 && pin_hold[i] != epoch && pin_stamp[i] < best) {
+                    best = pin_stamp[i];
+                    j = i;
+                }
+        }
+        if (j < 0) { err = "internal: no pin available for a reduction partner"; return 0; }
+        flush_rows();
+        uint32_t slot;
+        bool temp = false;
+        it = term_loc.find(v);
+        if (it != term_loc.end()) {
+            slot = it->second;  // resident in a tile slot
+        } else {
+            gen_term(v);
+            slot = (uint32_t)alloc_slot(-2);
+            emit(RI_ST, slot, 0.0, 0);
+            temp = true;
+        }
+        if (!err.empty()) return 0;
+        if (pin_term[j] >= 0) term_loc.erase(pin_term[j]);
+        emit(RI_PINB0 + (uint32_t)j, slot, 0.0, 0);
+        // the pin is the term's home from now on (operand register and reduction partner): the slot is released
+        if (!temp) term_loc.erase(v);
+        free_slot((int32_t)slot);
+        pin_term[j] = v;
+        pin_stamp[j] = clock++;
+        pin_hold[j] = epoch;
+        term_loc[v] = PINREF | (uint32_t)j;
+        return j;
+    }
+    // a row of the open group: term u against the pins in `pin_mask`, itself and ones. Appends the output ids in
+    // the order pins ascending, self, one.
+    void add_row(int32_t u, uint32_t pin_mask, bool self, bool one, bool keep, std::vector<int32_t> &ids)
+    {
+        if (rows.size() == 8) flush_rows();
+        uint32_t col;
+        bool free_after = false;
+        const Term &T = bp.term(u);
+        const TermNode &root = T.nodes.back();
+        auto it = term_loc.find(u);
+        if (it != term_loc.end() && !(it->second & PINREF)) {
+            col = it->second;
+            touch(col);
+        } else if (it != term_loc.end()) {
+            // resident as a pin only: a row needs the values in the tile
+            const int32_t sl = alloc_slot(-2);
+            emit(RI_LDP0 + (it->second & 0xff), 0, 0.0, 0);
+            emit(RI_ST, (uint32_t)sl, 0.0, 0);
+            col = (uint32_t)sl;
+            free_after = true;
+        } else if (root.op == RR_OP_VAR) {
+            col = staged(root.var);  // a bare feature is its own row: nothing to evaluate, nothing to store
+        } else {
+            gen_term(u);
+            const int32_t sl = alloc_slot(keep ? u : -2);
+            emit(RI_ST, (uint32_t)sl, 0.0, 0);
+            col = (uint32_t)sl;
+            free_after = !keep;
+        }
+        if (!err.empty()) return;
+        if (rows.size() == 8) flush_rows();  // (evaluating u can have flushed already; this is the size guard)
+        if (!(col & STAGED)) slot_rowheld[col] = 1;
+        GRow r;
+        r.col = col;
+        r.want = (pin_mask & 0xffu) | (self ? 1u << 8 : 0u) | (one ? 1u << 9 : 0u);
+        r.free_after = free_after;
+        rows.push_back(r);
+        for (int o = 0; o < 10; ++o)
+            if ((r.want >> o) & 1u) {
+                ids.push_back(P.n_dots);
+                P.n_dots += 1;
+                P.n_dot_ins += 1;
+            }
+    }
+
     int32_t clsmet(uint32_t y_ref)
     {
         emit(RI_CLSMET, y_ref, 0.0, 60);
@@ -815,12 +984,26 @@ struct BatchPlanner::Chunk {
 
     void close()
     {
+        if (g8) flush_rows();
         emit(RI_END, 0, 0.0, 0);
         const int32_t n_cols = (int32_t)colmap.size();
         auto patch = [&](uint32_t v) -> uint32_t { return (v & STAGED) ? (v & 0x3fffu) : (uint32_t)n_cols + v; };
         for (size_t i = pc_begin; i < P.ins.size(); ++i) {
             RRIns &x = P.ins[i];
             const uint32_t op = RR_OP(x.w0);
+            if (op == RI_GRAM8) {
+                // the column slot behind it: pre-patch bytes -> tile columns
+                RRIns &dsl = P.ins[i + 1];
+                uint8_t c8[8];
+                std::memcpy(c8, &dsl.w1, 4);
+                std::memcpy(c8 + 4, &dsl.imm, 4);
+                for (int g = 0; g < 8; ++g) c8[g] = (uint8_t)((c8[g] & 0x80u) ? (c8[g] & 0x7fu) : (uint32_t)n_cols + c8[g]);
+                std::memcpy(&dsl.w1, c8, 4);
+                std::memcpy(&dsl.imm, c8 + 4, 4);
+                ++i;
+                continue;
+            }
+            if (op == RI_PINBG) continue;  // w1 is an engine column
             bool has_col = op >= RI_FIRST_M || op == RI_ST || op == RI_CLSMET;
             if (op == RI_RARE) has_col = !(RR_AUX(x.w0) & RB_CONST);
             // the operand of the instruction after USEP comes from the pin: its column field stays 0
@@ -927,15 +1110,21 @@ struct BatchPlanner::Chunk {
             }
             P.ins.resize(pc_begin);
             P.ins.insert(P.ins.end(), out.begin(), out.end());
-            // second pass: "X; MDOT" -> X with RR_THEN_MDOT (the term's last operation runs into its reductions)
+            // second pass: "X; MDOT" -> X with RR_THEN_MDOT (the term's last operation runs into its reductions);
+            // G8 plans: "X; ST c" -> X with RR_THEN_ST (the term's last operation stores the row it has computed)
             out.clear();
             for (size_t i = pc_begin; i < P.ins.size(); ++i) {
                 RRIns x = P.ins[i];
                 const bool consumer_of_usep = !out.empty() && is_reg(RR_OP(out.back().w0), RI_USEP0);
-                if (!consumer_of_usep && rr_md_fusable(RR_OP(x.w0)) && RR_AUX(x.w0) == 0 && i + 1 < P.ins.size() &&
-                    RR_OP(P.ins[i + 1].w0) == RI_MDOT) {
-                    x.w0 |= RR_THEN_MDOT | (P.ins[i + 1].w0 & ~0xffu);
-                    ++i;
+                const bool data_slot = !out.empty() && RR_OP(out.back().w0) == RI_GRAM8;
+                if (!data_slot && !consumer_of_usep && rr_md_fusable(RR_OP(x.w0)) && RR_AUX(x.w0) == 0 && i + 1 < P.ins.size()) {
+                    if (!g8 && RR_OP(P.ins[i + 1].w0) == RI_MDOT) {
+                        x.w0 |= RR_THEN_MDOT | (P.ins[i + 1].w0 & ~0xffu);
+                        ++i;
+                    } else if (g8 && RR_OP(P.ins[i + 1].w0) == RI_ST && P.ins[i + 1].w1 < 256u) {
+                        x.w0 |= RR_THEN_ST | (P.ins[i + 1].w1 << 16);
+                        ++i;
+                    }
                 }
                 out.push_back(x);
             }
@@ -952,7 +1141,7 @@ struct BatchPlanner::Chunk {
             const uint32_t op = RR_OP(x.w0);
             return op == RI_MDOT || ((x.w0 & RR_THEN_MDOT) && rr_md_fusable(op));
         };
-        if (lim.mdot_rows) {
+        if (lim.mdot_rows && !g8) {
             std::vector<RRIns> out;
             out.reserve(P.ins.size() - pc_begin + 1024);
             uint32_t cnt = 0, fl = 0;  // reductions pushed / flushed, exactly as the kernel counts them
@@ -1006,7 +1195,8 @@ struct BatchPlanner::Chunk {
             nop.w0 = RI_NOP;
             for (size_t i = pc_begin; i < P.ins.size(); ++i) {
                 const uint32_t op = RR_OP(P.ins[i].w0);
-                const bool pair_head = (op >= RI_USEP0 && op < RI_USEP0 + RR_NREG) || (lim.mdot_rows && carries_mdot(P.ins[i]));
+                const bool pair_head = (op >= RI_USEP0 && op < RI_USEP0 + RR_NREG) || (lim.mdot_rows && !g8 && carries_mdot(P.ins[i])) ||
+                                       op == RI_GRAM8;
                 if (pair_head && out.size() % RR_INS_WINDOW == RR_INS_WINDOW - 1)
                     out.push_back(nop);
                 out.push_back(P.ins[i]);
@@ -1269,6 +1459,132 @@ std::string BatchPlanner::plan_gram(const PlanLimits &lim, const ColIds &cols, c
     return "";
 }
 
+// G8 variant of plan_gram (rr_isa.h RI_GRAM8): every term that still has reductions missing is evaluated into a tile
+// slot and becomes one ROW of the open group; its partners (the centred target and the candidate's other terms)
+// are pins; one RI_GRAM8 reduces up to eight rows against all pins with DMMA. A local-search neighbourhood keeps
+// its base terms pinned and contributes one row per candidate. Candidates with more than 8 terms need more partners
+// than there are pins: the caller plans those with plan_gram.
+std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> *subset, SweepPlan &P,
+                                       std::vector<int32_t> &cand_dot, std::vector<int32_t> &cand_dot_begin)
+{
+    std::vector<int32_t> list;
+    if (subset) list = *subset;
+    else {
+        list.resize(b_->n_cand);
+        for (int32_t c = 0; c < b_->n_cand; ++c) list[c] = c;
+    }
+    std::vector<Unit> units(list.size());
+    for (size_t i = 0; i < list.size(); ++i) {
+        const int32_t c = list[i];
+        for (int32_t t = b_->cand_term_begin[c]; t < b_->cand_term_begin[c + 1]; ++t)
+            units[i].terms.push_back(term_id_[t]);
+        units[i].w = cand_w_[c];
+        if ((int32_t)units[i].terms.size() > RR_NPIN) return "candidate too wide for a G8 plan";
+    }
+    std::vector<std::vector<int32_t>> term_units(terms_.size());
+    for (size_t i = 0; i < units.size(); ++i)
+        for (int32_t t : units[i].terms)
+            if (term_units[t].empty() || term_units[t].back() != (int32_t)i) term_units[t].push_back((int32_t)i);
+    const int32_t need = max_need(*this, units);
+    const int32_t min_slots = need + 1 + 2;  // spill temporaries + at least two rows
+    std::vector<ChunkSpec> specs;
+    std::vector<int32_t> always;
+    std::string err = cut_chunks(*this, units, lim, always, min_slots, specs);
+    if (!err.empty()) return err;
+
+    cand_dot.clear();
+    cand_dot_begin.assign(1, 0);
+    DotMap dots((size_t)units.size() * 8 + 64);
+    const int64_t KEY_YC = -1, KEY_ONE = -2;
+    auto key = [](int64_t a, int64_t b) -> uint64_t {
+        if (a > b) std::swap(a, b);
+        return ((uint64_t)(uint32_t)(int32_t)a << 32) | (uint64_t)(uint32_t)(int32_t)b;
+    };
+    std::vector<int32_t> ids;
+    for (const ChunkSpec &cs : specs) {
+        Chunk ch(*this, P, lim, cs.cols, RR_NPIN);
+        ch.g8 = true;
+        ch.reserve_pin_global(cols.yc);  // pin 0, for the whole chunk
+        for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
+            const std::vector<int32_t> &T = units[ui].terms;
+            const int32_t m = (int32_t)T.size();
+            auto missing = [&](int64_t a, int64_t b) { return dots.find(key(a, b)) == nullptr; };
+            std::vector<int32_t> N;
+            for (int32_t i = 0; i < m; ++i) {
+                bool miss = missing(T[i], KEY_YC) || missing(T[i], KEY_ONE);
+                for (int32_t j = 0; j < m && !miss; ++j) miss = missing(T[i], T[j]);
+                if (miss && std::find(N.begin(), N.end(), T[i]) == N.end()) N.push_back(T[i]);
+            }
+            // resident terms first: what is new in this candidate then meets all of its partners in its one row
+            std::stable_partition(N.begin(), N.end(), [&](int32_t u) { return ch.resident(u); });
+            ch.unpin_all();
+            std::vector<int32_t> done;
+            for (size_t q = 0; q < N.size(); ++q) {
+                const int32_t u = N[q];
+                const bool self = missing(u, u), one = missing(u, KEY_ONE), with_yc = missing(u, KEY_YC);
+                bool any = self || one || with_yc;
+                for (int32_t v : done)
+                    if (v != u && missing(u, v)) { any = true; break; }
+                if (!any) {
+                    // all of u's missing pairs are with terms that come later: u only has to be resident by then
+                    ch.ensure(u);
+                    done.push_back(u);
+                    if (!ch.err.empty()) return ch.err;
+                    continue;
+                }
+                uint32_t pin_mask = with_yc ? 1u : 0u;
+                uint64_t pin_key[RR_NPIN];
+                if (with_yc) pin_key[0] = key(u, KEY_YC);
+                for (int32_t v : done) {
+                    if (v == u || !missing(u, v)) continue;
+                    const int j = ch.pin_partner(v);
+                    if (!ch.err.empty()) return ch.err;
+                    if ((pin_mask >> j) & 1u) return "internal: duplicate pinned partner";
+                    pin_mask |= 1u << j;
+                    pin_key[j] = key(u, v);
+                }
+                bool transient = false;
+                if (q + 1 == N.size() && lim.transient_horizon > 0) {
+                    const std::vector<int32_t> &occ = term_units[u];
+                    auto it = std::upper_bound(occ.begin(), occ.end(), ui);
+                    transient = it == occ.end() || *it > ui + lim.transient_horizon;
+                }
+                ids.clear();
+                ch.add_row(u, pin_mask, self, one, !transient, ids);
+                if (!ch.err.empty()) return ch.err;
+                size_t k = 0;
+                for (int j = 0; j < RR_NPIN; ++j)
+                    if ((pin_mask >> j) & 1u) dots.set(pin_key[j], ids[k++]);
+                if (self) dots.set(key(u, u), ids[k++]);
+                if (one) dots.set(key(u, KEY_ONE), ids[k++]);
+                done.push_back(u);
+            }
+            for (int32_t i = 0; i < m; ++i)
+                for (int32_t j = i; j < m; ++j) {
+                    const int32_t *it = dots.find(key(T[i], T[j]));
+                    if (!it) return "internal: missing Gram dot";
+                    cand_dot.push_back(*it);
+                }
+            for (int32_t i = 0; i < m; ++i) {
+                const int32_t *it = dots.find(key(T[i], KEY_YC));
+                if (!it) return "internal: missing Gram dot";
+                cand_dot.push_back(*it);
+            }
+            for (int32_t i = 0; i < m; ++i) {
+                const int32_t *it = dots.find(key(T[i], KEY_ONE));
+                if (!it) return "internal: missing Gram dot";
+                cand_dot.push_back(*it);
+            }
+            cand_dot_begin.push_back((int32_t)cand_dot.size());
+        }
+        if (!ch.err.empty()) return ch.err;
+        ch.close();
+        P.n_gram_groups += ch.n_gram_groups;
+        P.n_gram_rows += ch.n_gram_rows;
+    }
+    return "";
+}
+
 std::string BatchPlanner::plan_residual(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> &subset,
                                         const double *coef, SweepPlan &P, std::vector<int32_t> &cand_dot,
                                         std::vector<int32_t> &cand_dot_begin)
@@ -1511,6 +1827,10 @@ extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kin
             err = bp.plan_residual(lim, cols, all, coef_snapped, P, tab, tab_begin);
             break;
         }
+        case 6:
+            lim.g8 = true;
+            err = bp.plan_gram_g8(lim, cols, nullptr, P, tab, tab_begin);
+            break;
         default: err = "bad kind";
         }
     }

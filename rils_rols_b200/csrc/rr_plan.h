@@ -54,6 +54,7 @@ struct SweepPlan {
     double w_issued = 0.0;      // contract-weighted FP64 work actually issued, per sample
     uint64_t n_term_evals = 0;
     uint64_t n_dot_ins = 0;
+    uint64_t n_gram_groups = 0, n_gram_rows = 0;  // G8 plans: RI_GRAM8 instructions and the rows they reduce
     bool empty() const { return chunks.empty(); }
 };
 
@@ -66,6 +67,7 @@ struct PlanLimits {
     int32_t transient_horizon = 4;  // a new term no candidate lists again within this many units is not stored
     bool no_cse = false;
     bool fuse = true;  // super-instruction peephole (rr_isa.h)
+    bool g8 = false;         // G8 plan (rr_isa.h RI_GRAM8): fresh terms in tile slots, reductions by DMMA against the pins
     bool mdot_rows = false;  // data slot with the ring rows behind every instruction that ends in RI_MDOT (rr_isa.h)
 };
 
@@ -98,6 +100,10 @@ public:
     std::string plan_gram(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> *subset,
                           bool dd, SweepPlan &out, std::vector<int32_t> &cand_dot,
                           std::vector<int32_t> &cand_dot_begin);
+
+    // the same for a G8 plan (candidates of at most RR_NPIN terms)
+    std::string plan_gram_g8(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> *subset, SweepPlan &out,
+                             std::vector<int32_t> &cand_dot, std::vector<int32_t> &cand_dot_begin);
 
     // explicit residual of the model sum_i cs_i t_i + cs_free (snapped coefficients, reference
     // association order) for the listed candidates: per candidate 1 (r.r) + m (r.t_i) + 1 (r.1) ids.

@@ -57,6 +57,8 @@ struct SweepArgs {
     double *stg;            // RI_STG target: column u at stg + u * ld_stg
     int64_t ld_stg;
     int32_t dd_ring;        // double-double plans: 1 = warp reduction through the ring, 0 = shuffle tree
+    int32_t tile_dbuf;      // 1 = two tile buffers of tile_buf_doubles each: the next tile's columns are fetched while this one runs
+    int64_t tile_buf_doubles;
     int32_t n_tiles;        // < 0: probe, the kernel only reports the shared-window address of its dynamic part in acc[0]
 };
 
@@ -215,11 +217,11 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     constexpr uint32_t HALFB = T * 4u;  // byte offset of the second half of a column
     extern __shared__ __align__(128) unsigned char rr_dyn[];  // [slack][rings: NW x 16 rows x 32 lanes][tile: columns x T]
     __shared__ __align__(16) unsigned char rr_static[kSweepStaticBytes];
-    static_assert(2 * (kInsWindow + 2) * 16 + 3 * 8 <= kSweepStaticBytes, "static shared memory layout");
+    static_assert(2 * (kInsWindow + 2) * 16 + 4 * 8 <= kSweepStaticBytes, "static shared memory layout");
     // each window is followed by its sentinel and one padding slot (the core prefetches one instruction ahead)
     uint4(*ibuf)[kInsWindow + 2] = reinterpret_cast<uint4(*)[kInsWindow + 2]>(rr_static);
-    uint64_t &mbar_tile = *reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16);
-    uint64_t *mbar_ins = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16 + 8);
+    uint64_t *mbar_tile = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16);  // one per tile buffer
+    uint64_t *mbar_ins = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16 + 16);
 
     if (a.n_tiles < 0) {
         if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.acc[0] = (double)smem_u32(rr_dyn);
@@ -237,8 +239,11 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     const uint32_t dyn_sh = smem_u32(rr_dyn);
     const uint32_t ring_sh = (dyn_sh + 4095u) & ~4095u;  // rings of warps 0..NW-1, each 4096-aligned
     const uint32_t stage_sh = ring_sh + NW * 4096u;          // staging rows: 256 bytes per warp
-    double *const rr_tile = reinterpret_cast<double *>(rr_dyn + (ring_sh - dyn_sh) + NW * (4096u + 256u));
-    const uint32_t tile_sh = stage_sh + NW * 256u + tbase;
+    double *const rr_tile0 = reinterpret_cast<double *>(rr_dyn + (ring_sh - dyn_sh) + NW * (4096u + 256u));
+    const uint32_t tile_sh0 = stage_sh + NW * 256u + tbase;
+    const bool dbuf = a.tile_dbuf != 0;
+    // a program of one window stays in its buffer for the whole launch instead of being fetched again for every tile
+    const bool resident_prog = n_win == 1;
     RingCtx rc;
     rc.lane = (uint32_t)lane;
     rc.warp = (uint32_t)warp;
@@ -257,7 +262,8 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                  ch.dot_base;
 
     if (tid == 0) {
-        mbar_init(&mbar_tile, 1);
+        mbar_init(&mbar_tile[0], 1);
+        mbar_init(&mbar_tile[1], 1);
         mbar_init(&mbar_ins[0], 1);
         mbar_init(&mbar_ins[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -268,25 +274,50 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         ibuf[1][kInsWindow + 1] = make_uint4(RI_END, 0, 0, 0);
     }
     __syncthreads();
-    uint32_t tile_parity = 0, ins_parity0 = 0, ins_parity1 = 0;
-
-    for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
-        const int64_t base = (int64_t)tile_i * T;
-        if (warp == 0) {
-            // order this block's earlier generic-proxy accesses to the tile before the async writes
+    uint32_t tile_parity[2] = {0u, 0u}, ins_parity0 = 0, ins_parity1 = 0;
+    // warp 0 fetches the staged columns of tile `ti` into tile buffer `bf` (TMA bulk copies on that buffer's mbarrier)
+    auto fetch_tile = [&](int ti, int bf) {
+        // order this block's earlier generic-proxy accesses to the buffer before the async writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) mbar_expect_tx(&mbar_tile[bf], (uint32_t)(ch.n_cols * T * 8));
+        __syncwarp();
+        double *dst = rr_tile0 + (size_t)bf * a.tile_buf_doubles;
+        const int64_t b0 = (int64_t)ti * T;
+        for (int c = lane; c < ch.n_cols; c += 32)
+            tma_load_1d(dst + (size_t)c * T, a.X + (size_t)a.cols[ch.col_begin + c] * a.ld + b0, (uint32_t)(T * 8), &mbar_tile[bf]);
+    };
+    if (resident_prog) {
+        if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (lane == 0) {
-                mbar_expect_tx(&mbar_tile, (uint32_t)(ch.n_cols * T * 8));
+            mbar_expect_tx(&mbar_ins[0], (uint32_t)(kInsWindow * 16));
+            tma_load_1d(&ibuf[0][0], prog, (uint32_t)(kInsWindow * 16), &mbar_ins[0]);
+        }
+        mbar_wait(&mbar_ins[0], 0u);
+    }
+    if (dbuf && warp == 0 && (int)blockIdx.x < a.n_tiles) fetch_tile(blockIdx.x, 0);
+
+    int it = 0;
+    for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x, ++it) {
+        const int64_t base = (int64_t)tile_i * T;
+        const int bf = dbuf ? (it & 1) : 0;
+        double *const rr_tile = rr_tile0 + (size_t)bf * a.tile_buf_doubles;
+        (void)rr_tile;
+        const uint32_t tile_sh = tile_sh0 + (uint32_t)bf * (uint32_t)(a.tile_buf_doubles * 8);
+        if (warp == 0) {
+            if (dbuf) {
+                // the other buffer was last read in the previous iteration, which ended in a block barrier
+                if (tile_i + (int)gridDim.x < a.n_tiles) fetch_tile(tile_i + (int)gridDim.x, bf ^ 1);
+            } else {
+                fetch_tile(tile_i, 0);
+            }
+            if (!resident_prog && lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&mbar_ins[0], (uint32_t)(kInsWindow * 16));
                 tma_load_1d(&ibuf[0][0], prog, (uint32_t)(kInsWindow * 16), &mbar_ins[0]);
             }
-            __syncwarp();
-            for (int c = lane; c < ch.n_cols; c += 32)
-                tma_load_1d(rr_tile + (size_t)c * T, a.X + (size_t)a.cols[ch.col_begin + c] * a.ld + base,
-                            (uint32_t)(T * 8), &mbar_tile);
         }
-        mbar_wait(&mbar_tile, tile_parity);
-        tile_parity ^= 1u;
+        mbar_wait(&mbar_tile[bf], tile_parity[bf]);
+        tile_parity[bf] ^= 1u;
 
         const bool partial = base + T > a.n;
         bool valid[S];
@@ -343,16 +374,18 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         bool running = true;
         for (int win = 0; running; ++win) {
             const int b = win & 1;
-            // every warp has finished window win-1, so its buffer (the other one) may be refilled
-            __syncthreads();
-            if (tid == 0 && win + 1 < n_win) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&mbar_ins[b ^ 1], (uint32_t)(kInsWindow * 16));
-                tma_load_1d(&ibuf[b ^ 1][0], prog + (size_t)(win + 1) * kInsWindow, (uint32_t)(kInsWindow * 16),
-                            &mbar_ins[b ^ 1]);
+            if (!resident_prog) {
+                // every warp has finished window win-1, so its buffer (the other one) may be refilled
+                __syncthreads();
+                if (tid == 0 && win + 1 < n_win) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&mbar_ins[b ^ 1], (uint32_t)(kInsWindow * 16));
+                    tma_load_1d(&ibuf[b ^ 1][0], prog + (size_t)(win + 1) * kInsWindow, (uint32_t)(kInsWindow * 16),
+                                &mbar_ins[b ^ 1]);
+                }
+                if (b == 0) { mbar_wait(&mbar_ins[0], ins_parity0); ins_parity0 ^= 1u; }
+                else { mbar_wait(&mbar_ins[1], ins_parity1); ins_parity1 ^= 1u; }
             }
-            if (b == 0) { mbar_wait(&mbar_ins[0], ins_parity0); ins_parity0 ^= 1u; }
-            else { mbar_wait(&mbar_ins[1], ins_parity1); ins_parity1 ^= 1u; }
             const uint4 *ib = ibuf[b];
             if constexpr (!SPECIAL && PAIRS && NW == 4) {
                 if (!partial) {
@@ -456,7 +489,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                     if ((w0 & RR_THEN_MDOT) && op >= RI_MULP0) mdot(w0);
                     continue;
                 }
-                if (op >= RI_LDPMUL_M0) {
+                if (op >= RI_LDPMUL_M0 && op < RI_PINB0) {
                     // fused register / tile-column forms: LDPMUL_M, LDPDIV_M, LDMDIVP
                     const int j = (int)((op - RI_LDPMUL_M0) % RR_NREG);
                     const uint32_t kind = (op - RI_LDPMUL_M0) / RR_NREG;

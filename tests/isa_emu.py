@@ -18,7 +18,8 @@ from rils_rols_b200.batch import Batch, rr_batch
 RR_NPIN = 8
 RR_NREG = 10
 (RI_END, RI_WINEND, RI_LOAD_C, RI_ST, RI_STG, RI_LDG, RI_NOP, RI_COMBINE, RI_ADD_C, RI_SUB_C, RI_RSUB_C, RI_MUL_C, RI_DIV_C,
- RI_RDIV_C, RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR, RI_RARE, RI_MDOT, RI_MDOTDD, RI_CLSMET, RI_PIN0) = range(25)
+ RI_RDIV_C, RI_SIN, RI_COS, RI_LN, RI_EXP, RI_SQRT, RI_SQR, RI_RARE, RI_MDOT, RI_GRAM8, RI_PINBG, RI_MDOTDD, RI_CLSMET,
+ RI_PIN0) = range(27)
 RR_INS_WINDOW = 64
 RI_LDP0 = RI_PIN0 + RR_NREG
 RI_USEP0 = RI_LDP0 + RR_NREG
@@ -32,12 +33,15 @@ RI_FIRST_M = RI_CDIVP0 + RR_NREG
  RI_DOTMDD, RI_CMUL_M, RI_CDIV_M, RI_MUL_MM, RI_MUL_M_ST, RI_LDPMUL_M0) = range(RI_FIRST_M, RI_FIRST_M + 15)
 RI_LDPDIV_M0 = RI_LDPMUL_M0 + RR_NREG
 RI_LDMDIVP0 = RI_LDPDIV_M0 + RR_NREG
-RI_OPCOUNT = RI_LDMDIVP0 + RR_NREG
+RI_PINB0 = RI_LDMDIVP0 + RR_NREG
+RI_OPCOUNT = RI_PINB0 + RR_NPIN
 RR_MDOT_MAX_OUT = 8
 RR_POW, RR_LT, RR_GT, RR_EQ, RR_NE, RR_MIN, RR_MAX = range(7)
 RB_CONST, RB_SWAP = 1 << 4, 1 << 5
 RR_THEN_MDOT = 0x8000
+RR_THEN_ST = 0x8000  # G8 plans: the same bit means "X; ST c", c in bits 16-23 of w0
 RR_MDOT_ROWS = 1
+RR_GRAM_COLS = 2
 
 
 def ring_rows(aux: int, cnt: int):
@@ -59,14 +63,14 @@ def ring_rows(aux: int, cnt: int):
 
 def md_fusable(op: int) -> bool:
     return (op in (RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_DIV_C, RI_RDIV_C, RI_CMUL_M, RI_CDIV_M, RI_MUL_MM)
-            or RI_MULP0 <= op < RI_FIRST_M or RI_LDPMUL_M0 <= op < RI_OPCOUNT)
+            or RI_MULP0 <= op < RI_FIRST_M or RI_LDPMUL_M0 <= op < RI_PINB0)
 
 
 INS_DT = np.dtype([("w0", "<u4"), ("w1", "<u4"), ("imm", "<f8")])
 CHUNK_DT = np.dtype([("pc_begin", "<i4"), ("n_ins", "<i4"), ("dot_base", "<i4"), ("n_dots", "<i4"),
                      ("col_begin", "<i4"), ("n_cols", "<i4"), ("r0", "<i4"), ("r1", "<i4")])
 
-KIND_GRAM, KIND_GRAM_DD, KIND_EVAL, KIND_EVAL_METRICS, KIND_MATERIALISE, KIND_RESIDUAL = range(6)
+KIND_GRAM, KIND_GRAM_DD, KIND_EVAL, KIND_EVAL_METRICS, KIND_MATERIALISE, KIND_RESIDUAL, KIND_GRAM_G8 = range(7)
 
 
 class rr_debug_plan(C.Structure):
@@ -123,6 +127,8 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
     n = cols_global.shape[1]
     dots = np.zeros(max(plan.n_dots, 1))
     stg = np.zeros((n_stg, n))
+    n_gram = [0, 0]  # GRAM8 instructions, rows
+    plan.gram_stats = n_gram
 
     def do_mdot(op, aux, t, pins, out):
         step = 2 if op == RI_MDOTDD else 1
@@ -244,7 +250,38 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     assert col2 < plan.max_tile_cols, f"tile column {col2} out of range"
                     t = t * src
                     tile[col2] = t.copy()
-                elif RI_LDPMUL_M0 <= op < RI_OPCOUNT:
+                elif op == RI_GRAM8:
+                    # up to 8 rows (tile columns named by the column slot behind the instruction) against the 8 pins,
+                    # themselves and ones; wanted outputs in bit order take consecutive ids
+                    assert plan.kind == KIND_GRAM_G8
+                    n_rows = aux & 0xFF
+                    assert 1 <= n_rows <= 8
+                    assert (pc - 1 - int(ch["pc_begin"])) % RR_INS_WINDOW != RR_INS_WINDOW - 1, "GRAM8 at a window end"
+                    bits = w1 | (int(plan.ins["imm"][pc - 1:pc].view(np.uint64)[0]) << 32)
+                    d0 = int(plan.ins["w0"][pc])
+                    assert (d0 & 0xFFFF) == (RI_NOP | RR_GRAM_COLS << 8), "GRAM8 without its column slot"
+                    cols8 = list(plan.ins[pc:pc + 1].view(np.uint8)[4:12])
+                    pc += 1
+                    assert bits >> (10 * n_rows) == 0, "wanted bits beyond the last row"
+                    for g in range(n_rows):
+                        assert cols8[g] < plan.max_tile_cols, f"row column {cols8[g]} out of range"
+                        a = tile[cols8[g]]
+                        for o in range(10):
+                            if bits >> (10 * g + o) & 1:
+                                if o < 8:
+                                    assert pins[o] is not None, "GRAM8 against an empty pin"
+                                    v = float(np.dot(a, pins[o]))
+                                else:
+                                    v = float(np.dot(a, a)) if o == 8 else float(np.sum(a))
+                                dots[out] += v
+                                out += 1
+                    n_gram[0] += 1
+                    n_gram[1] += n_rows
+                elif op == RI_PINBG:
+                    pins[aux & 0xFF] = cols_global[w1].copy()
+                elif RI_PINB0 <= op < RI_PINB0 + RR_NPIN:
+                    pins[op - RI_PINB0] = src.copy()
+                elif RI_LDPMUL_M0 <= op < RI_PINB0:
                     j = (op - RI_LDPMUL_M0) % RR_NREG
                     assert pins[j] is not None, "fused form reads an empty value register"
                     kind = (op - RI_LDPMUL_M0) // RR_NREG
@@ -284,7 +321,11 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     ring_cnt += 3
                 else:
                     raise AssertionError(f"bad opcode {op}")
-                if (w0 & RR_THEN_MDOT) and md_fusable(op):  # "X; MDOT" in one instruction
+                if (w0 & RR_THEN_ST) and md_fusable(op) and plan.kind == KIND_GRAM_G8:  # "X; ST c" in one instruction
+                    c = (w0 >> 16) & 0xFF
+                    assert c < plan.max_tile_cols, f"tile column {c} out of range"
+                    tile[c] = t.copy()
+                elif (w0 & RR_THEN_MDOT) and md_fusable(op):  # "X; MDOT" in one instruction
                     out = do_mdot(RI_MDOT, aux & ~(RR_THEN_MDOT >> 8), t, pins, out)
                     if ring_cnt - ring_fl >= 8:
                         ring_fl += 8

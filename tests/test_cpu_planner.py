@@ -367,3 +367,65 @@ def test_deep_trees_spill_into_slots():
     code, consts = e.program()
     want = float(((y - O.evaluate(O.feature_major(X), code, consts)) ** 2).sum())
     assert abs(dots[plan.tab[0]] - want) <= 1e-12 * want
+
+
+def narrow_subset(batch, limit=None):
+    """candidates with at most 8 terms (what a G8 plan takes; the engine plans the wider ones the classic way)"""
+    m = np.diff(batch.cand_term_begin)
+    idx = [int(c) for c in np.nonzero(m <= 8)[0]]
+    return idx[:limit] if limit else idx
+
+
+@pytest.mark.parametrize("tile_cols", [26, 8, 5])
+@pytest.mark.parametrize("cfg,prefix", [("cfg1_toy", "ls3_"), ("cfg3_breast_cancer", "ls0_"), ("cfg5", "")])
+def test_g8_plan_reproduces_design_matrix_products(golden, cfg, prefix, tile_cols):
+    """G8 plans (rr_isa.h RI_GRAM8: rows in tile slots reduced eight at a time against the pins): every Gram / A^T yc /
+    column-sum entry the solver reads must be the design-matrix product, with plenty of tile slots and with very few
+    (groups then close early), and the plan must be the classic plan's equal in shared work."""
+    if cfg == "cfg5":
+        from rils_rols_b200 import workloads as W
+
+        full = W.cfg5_neighbourhood()
+        X, y = W.cfg5_data(300)
+    else:
+        z = golden(cfg)
+        X, y = z["X"], z["y"]
+        full = B.Batch.load_fields(z, prefix)
+    batch = full.subset(narrow_subset(full, 500))
+    d = X.shape[1]
+    tc = tile_cols + (d if tile_cols < 26 else 0)  # slots on top of the staged features
+    if cfg == "cfg3_breast_cancer" and tile_cols == 26:
+        tc = 40
+    plan = EMU.Plan(batch, d, EMU.KIND_GRAM_G8, tile_cols=tc)
+    classic = EMU.Plan(batch, d, EMU.KIND_GRAM, tile_cols=56)
+    assert plan.max_tile_cols <= tc
+    ops = _opcodes(plan)
+    assert (ops == EMU.RI_GRAM8).any() and not (ops == EMU.RI_MDOT).any() and not (ops == EMU.RI_DOTM).any()
+    assert plan.n_dots == classic.n_dots  # the same distinct reductions, each once
+    G_cols = EMU.engine_columns(X, y)
+    dots, _ = EMU.run(plan, G_cols)
+    groups, rows = plan.gram_stats
+    assert groups >= 1 and rows >= groups
+    if tile_cols == 26 and cfg != "cfg1_toy":
+        assert rows / groups > 3.0, (groups, rows)  # a local-search neighbourhood fills its groups
+    Xfm = O.feature_major(X)
+    yc = y - y.mean()
+    with np.errstate(all="ignore"):
+        for c in range(0, batch.n_cand, 5):
+            A = design(Xfm, batch, c)
+            G, byc = gram_from_dots(plan, dots, batch, c, X.shape[0])
+            want = A.T @ A
+            ok = np.isclose(G, want, rtol=1e-12, atol=0, equal_nan=True) | (~np.isfinite(want) & ~np.isfinite(G))
+            assert ok.all(), f"cand {c}"
+            wb = A[:, :-1].T @ yc
+            okb = np.isclose(byc, wb, rtol=1e-10, atol=1e-9 * np.abs(yc).sum(), equal_nan=True) | (~np.isfinite(wb) & ~np.isfinite(byc))
+            assert okb.all(), f"cand {c}"
+    print(f"\n{cfg} tile_cols={tc}: {len(plan.ins)} instructions (classic {len(classic.ins)}), {groups} GRAM8 with {rows} rows "
+          f"({rows / groups:.2f} per group), w_issued {plan.w_issued:.0f} (classic {classic.w_issued:.0f})")
+
+
+def test_g8_plan_rejects_wide_candidates():
+    v = B.Expr.var
+    wide = B.Batch.from_exprs(B.MODE_OLS_FIT, [[v(i % 3) * float(i + 2) + B.sin(v(i % 3) * float(i)) for i in range(9)]])
+    with pytest.raises(ValueError, match="too wide"):
+        EMU.Plan(wide, 3, EMU.KIND_GRAM_G8, tile_cols=26)

@@ -415,7 +415,9 @@ def test_predict_streams_through_the_engine_and_predict_proba():
         t = time.perf_counter()
         got = eng.predict(code, consts, X)
         dt = time.perf_counter() - t
-        assert np.allclose(got, want, rtol=1e-14, atol=0) and eng.stats()["kernel_launches"] > l0
+        # sin / ln come from the device fast paths (<= 1 ulp from correctly rounded, glibc likewise): a few ulps of the
+        # largest addend
+        assert np.allclose(got, want, rtol=1e-14, atol=1e-14 * np.abs(want).max()) and eng.stats()["kernel_launches"] > l0
         got_fm = eng.predict(code, consts, np.ascontiguousarray(X.T), rowmajor=False)
         assert np.array_equal(got, got_fm)
         os.environ["RR_B200_PREDICT_CHUNK_BYTES"] = str(8 * d * 70001)
