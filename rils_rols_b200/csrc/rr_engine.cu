@@ -1090,11 +1090,53 @@ int run_exact(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *
     const size_t per_cand = ((size_t)n * (kmax + 1)) * 8;
     int Q = (int)std::min<size_t>((size_t)nc, std::max<size_t>(32, budget / per_cand));
     Q = (int)round_up(Q, 32);
+    const double *ycol = e->X.as<double>() + (size_t)e->d * e->ld;
+    // One warp per candidate with the matrix in shared memory (rr_exact_qr_warp) whenever a candidate's matrix fits:
+    // candidates are bucketed by column count so that one outlier (expand() can blow a candidate up to dozens of
+    // terms) does not cost every warp its shared memory. Larger n: one thread per candidate in global memory.
+    const size_t smem_cap = 200 * 1024;
+    auto per_warp_bytes = [&](int kcap) { return ((size_t)n * (kcap + 1) + 5 * (size_t)kcap + (size_t)(kcap + 1) / 2 + 1) * 8; };
+    const int kcap_a = std::min(kmax, 12);
+    const int wpb_a = (int)std::min<size_t>(8, smem_cap / per_warp_bytes(kcap_a));
+    const int wpb_b = (int)std::min<size_t>(8, smem_cap / per_warp_bytes(kmax));
+    const bool warp_path = wpb_a >= 1 && wpb_b >= 1 && env_int("RR_B200_EXACT_WARP", 1) != 0;
+    if (warp_path) {
+        std::vector<int32_t> la, lb;
+        for (int c = 0; c < nc; ++c) (bp.k_of(c) <= kcap_a ? la : lb).push_back(c);
+        std::vector<int32_t> both(la);
+        both.insert(both.end(), lb.begin(), lb.end());
+        if ((rc = upload(e, e->d_list, both.data(), both.size()))) return rc;
+        rr::ExactArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.V = e->d_V.as<double>();
+        a.ldv = e->ld;
+        a.y = ycol;
+        a.n = n;
+        a.term_ids = e->d_tid.as<int32_t>();
+        a.cand_term_begin = e->d_ctb.as<int32_t>();
+        a.kmax = kmax;
+        a.coef = e->d_coef.as<double>();
+        a.nzp = e->d_nzp.as<int32_t>();
+        a.flags = e->d_flags.as<uint32_t>();
+        CU(cudaFuncSetAttribute(rr::rr_exact_qr_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        struct Bucket { size_t begin, count; int kcap, wpb; };
+        for (const Bucket &bk : {Bucket{0, la.size(), kcap_a, wpb_a}, Bucket{la.size(), lb.size(), kmax, wpb_b}}) {
+            if (!bk.count) continue;
+            rr::ExactWarpArgs w;
+            w.a = a;
+            w.list = e->d_list.as<int32_t>() + bk.begin;
+            w.n_list = (int32_t)bk.count;
+            w.kcap = bk.kcap;
+            const size_t smem = per_warp_bytes(bk.kcap) * bk.wpb;
+            rr::rr_exact_qr_warp<<<(unsigned)((bk.count + bk.wpb - 1) / bk.wpb), bk.wpb * 32, smem, e->stream>>>(w);
+            CU(cudaGetLastError());
+            e->stats.kernel_launches++;
+        }
+    } else {
     CU(e->d_A.ensure((size_t)n * kmax * Q * 8));
     CU(e->d_rhs.ensure((size_t)n * Q * 8));
     CU(e->d_aux.ensure((size_t)Q * 5 * kmax * 8));
     CU(e->d_perm.ensure((size_t)Q * kmax * 4));
-    const double *ycol = e->X.as<double>() + (size_t)e->d * e->ld;
     for (int lo = 0; lo < nc; lo += Q) {
         rr::ExactArgs a;
         a.V = e->d_V.as<double>();
@@ -1118,6 +1160,7 @@ int run_exact(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *
         rr::rr_exact_qr<<<(a.cand_hi - lo + threads - 1) / threads, threads, 0, e->stream>>>(a);
         CU(cudaGetLastError());
         e->stats.kernel_launches++;
+    }
     }
     rr::ResidColsArgs r;
     r.V = e->d_V.as<double>();

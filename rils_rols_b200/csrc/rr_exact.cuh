@@ -183,6 +183,196 @@ __global__ void rr_exact_qr(const ExactArgs a)
 #undef RHS
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same algorithm, one WARP per candidate, the matrix in shared memory.
+//
+// One thread per candidate in global memory (above) leaves a neighbourhood of 800 candidates with 25 warps on 148
+// SMs, each waiting on memory at every step (9 ms per neighbourhood at n = 331: all the GPU time of a fit() on the
+// small BASELINE configs). Here a warp owns a candidate and keeps A (rows x cols, column-major) and y in shared
+// memory. Parity with the sequential algorithm is kept operation by operation:
+//   * every SUM (column norms, the reflector's tail norm, v'A_j, the norm recomputation, v'b) is still one
+//     sequential chain in row order - the chains of different columns run in different lanes, a chain that is needed
+//     by the whole warp is computed by every lane redundantly (same operands, same order, same bits);
+//   * everything elementwise (column swap, scaling by 1/(c0 - beta), the rank-1 update, the updates of b) is spread
+//     over the lanes: each element is produced by the same expression as in the sequential code.
+// So the results are bit-identical to rr_exact_qr's (tests/test_gpu_golden.py compares both with the oracle).
+struct ExactWarpArgs {
+    ExactArgs a;
+    const int32_t *list;  // candidates of this launch
+    int32_t n_list;
+    int32_t kcap;         // column capacity of a warp's shared-memory matrix (>= cols of every listed candidate)
+};
+
+__device__ __forceinline__ size_t exact_warp_smem_doubles(int rows, int kcap) { return (size_t)rows * (kcap + 1) + 5 * (size_t)kcap; }
+
+__global__ void rr_exact_qr_warp(const ExactWarpArgs w)
+{
+    extern __shared__ __align__(16) double rr_ex_smem[];
+    const ExactArgs &a = w.a;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int li = blockIdx.x * wpb + warp;
+    if (li >= w.n_list) return;
+    const int c = w.list[li];
+    const int rows = a.n;
+    const int m = a.cand_term_begin[c + 1] - a.cand_term_begin[c];
+    const int cols = m + 1;
+    const size_t per_warp = exact_warp_smem_doubles(rows, w.kcap) + (size_t)((w.kcap + 1) / 2 + 1);
+    double *A = rr_ex_smem + (size_t)warp * per_warp;  // column j at A + j * rows
+    double *rhs = A + (size_t)rows * w.kcap;
+    double *hcoef = rhs + rows, *work = hcoef + w.kcap, *nu = work + w.kcap, *nd = nu + w.kcap, *x = nd + w.kcap;
+    int *perm = reinterpret_cast<int *>(x + w.kcap);
+#define AT(i, j) A[(size_t)(j) * rows + (i)]
+
+    // rils_rols_cpp.cpp:477-482: A.col(i) = factors[i]->evaluate_all(X), last column = ones
+    for (int j = 0; j < m; ++j) {
+        const double *src = a.V + (int64_t)a.term_ids[a.cand_term_begin[c] + j] * a.ldv;
+        for (int i = lane; i < rows; i += 32) AT(i, j) = src[i];
+    }
+    for (int i = lane; i < rows; i += 32) {
+        AT(i, m) = 1.0;
+        rhs[i] = a.y[i];
+    }
+    __syncwarp();
+
+    const int size = rows < cols ? rows : cols;
+    // ColPivHouseholderQR.h:504-509: one column per lane, each sum sequential in row order
+    for (int k = lane; k < cols; k += 32) {
+        double s = 0.0;
+        for (int i = 0; i < rows; ++i) s += AT(i, k) * AT(i, k);
+        nd[k] = sqrt(s);
+        nu[k] = nd[k];
+        perm[k] = k;
+    }
+    __syncwarp();
+    double maxnorm = nu[0];
+    for (int k = 1; k < cols; ++k)
+        if (nu[k] > maxnorm) maxnorm = nu[k];
+    const double threshold_helper = (maxnorm * DBL_EPSILON) * (maxnorm * DBL_EPSILON) / (double)rows;  // :511
+    const double norm_downdate_threshold = sqrt(DBL_EPSILON);
+    int nonzero_pivots = size;
+
+    for (int k = 0; k < size; ++k) {
+        // pivot search: every lane, same data (broadcast reads)
+        int big = k;
+        double bigv = nu[k];
+        for (int j = k + 1; j < cols; ++j)
+            if (nu[j] > bigv) { bigv = nu[j]; big = j; }
+        if (nonzero_pivots == size && bigv * bigv < threshold_helper * (double)(rows - k)) nonzero_pivots = k;  // :526
+        __syncwarp();
+        if (k != big) {  // :530-536
+            for (int i = lane; i < rows; i += 32) { const double t = AT(i, k); AT(i, k) = AT(i, big); AT(i, big) = t; }
+            if (lane == 0) {
+                double t = nu[k]; nu[k] = nu[big]; nu[big] = t;
+                t = nd[k]; nd[k] = nd[big]; nd[big] = t;
+                const int ti = perm[k]; perm[k] = perm[big]; perm[big] = ti;
+            }
+            __syncwarp();
+        }
+        // makeHouseholderInPlace, Householder.h:67-98: the tail norm is one chain, computed by every lane
+        const int mlen = rows - k;
+        double tail_sq = 0.0;
+        for (int i = 1; i < mlen; ++i) tail_sq += AT(k + i, k) * AT(k + i, k);
+        const double c0 = AT(k, k);
+        double beta, tau;
+        __syncwarp();
+        if (tail_sq <= DBL_MIN) {
+            tau = 0.0;
+            beta = c0;
+            for (int i = 1 + lane; i < mlen; i += 32) AT(k + i, k) = 0.0;
+        } else {
+            beta = sqrt(c0 * c0 + tail_sq);
+            if (c0 >= 0.0) beta = -beta;
+            const double denom = c0 - beta;
+            for (int i = 1 + lane; i < mlen; i += 32) AT(k + i, k) = AT(k + i, k) / denom;
+            tau = (beta - c0) / beta;
+        }
+        if (lane == 0) {
+            hcoef[k] = tau;
+            AT(k, k) = beta;
+        }
+        __syncwarp();
+        // applyHouseholderOnTheLeft to the trailing columns, Householder.h:116-135
+        if (cols - k - 1 > 0) {
+            if (mlen == 1) {
+                for (int j = k + 1 + lane; j < cols; j += 32) AT(k, j) *= (1.0 - tau);
+            } else if (tau != 0.0) {
+                for (int j = k + 1 + lane; j < cols; j += 32) {  // v'A_j: one chain per column, one column per lane
+                    double s = 0.0;
+                    for (int i = 1; i < mlen; ++i) s += AT(k + i, k) * AT(k + i, j);
+                    work[j] = s + AT(k, j);
+                }
+                __syncwarp();
+                for (int j = k + 1; j < cols; ++j) {
+                    const double wj = work[j];
+                    for (int i = lane; i < mlen; i += 32) {
+                        if (i == 0) AT(k, j) -= tau * wj;
+                        else AT(k + i, j) -= (tau * AT(k + i, k)) * wj;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // norm downdate, ColPivHouseholderQR.h:553-573: one column per lane
+        for (int j = k + 1 + lane; j < cols; j += 32) {
+            if (nu[j] != 0.0) {
+                double temp = fabs(AT(k, j)) / nu[j];
+                temp = (1.0 + temp) * (1.0 - temp);
+                temp = temp < 0.0 ? 0.0 : temp;
+                const double ratio = nu[j] / nd[j];
+                const double temp2 = temp * (ratio * ratio);
+                if (temp2 <= norm_downdate_threshold) {
+                    double s = 0.0;
+                    for (int i = k + 1; i < rows; ++i) s += AT(i, j) * AT(i, j);
+                    nd[j] = sqrt(s);
+                    nu[j] = nd[j];
+                } else {
+                    nu[j] *= sqrt(temp);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // _solve_impl, ColPivHouseholderQR.h:587-607
+    double *coef = a.coef + a.cand_term_begin[c] + c;
+    if (nonzero_pivots == 0) {
+        for (int j = lane; j < cols; j += 32) coef[j] = 0.0;
+    } else {
+        for (int k = 0; k < nonzero_pivots; ++k) {
+            const int mlen = rows - k;
+            const double tau = hcoef[k];
+            if (mlen == 1) {
+                if (lane == 0) rhs[k] *= (1.0 - tau);
+            } else if (tau != 0.0) {
+                double s = 0.0;  // v'b: one chain, every lane
+                for (int i = 1; i < mlen; ++i) s += AT(k + i, k) * rhs[k + i];
+                const double tmp = s + rhs[k];
+                __syncwarp();
+                for (int i = lane; i < mlen; i += 32) {
+                    if (i == 0) rhs[k] -= tau * tmp;
+                    else rhs[k + i] -= (tau * AT(k + i, k)) * tmp;
+                }
+            }
+            __syncwarp();
+        }
+        for (int i = nonzero_pivots - 1; i >= 0; --i) {
+            const double xi = rhs[i] / AT(i, i);
+            __syncwarp();
+            if (lane == 0) rhs[i] = xi;
+            for (int j = lane; j < i; j += 32) rhs[j] -= xi * AT(j, i);
+            __syncwarp();
+        }
+        for (int i = lane; i < cols; i += 32) x[perm[i]] = i < nonzero_pivots ? rhs[i] : 0.0;
+        __syncwarp();
+        for (int j = lane; j < cols; j += 32) coef[j] = x[j];
+    }
+    if (lane == 0) {
+        a.nzp[c] = nonzero_pivots;
+        a.flags[c] = RR_RES_EXACT | (nonzero_pivots < size ? RR_RES_RANKDEF : 0u);
+    }
+#undef AT
+}
+
 struct ResidColsArgs {
     const double *V;
     int64_t ldv;
