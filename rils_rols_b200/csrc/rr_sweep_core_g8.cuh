@@ -129,14 +129,16 @@ static_assert(RI_OPCOUNT == 158, "update the jump table of rr_core_g8");
 #define RR_G8_OFFV_14 "448"
 #define RR_G8_OFFV_15 "480"
 // one step of the group: A element from the row's slot, DMMA against the B fragment, the row's own t.t and sum(t)
-#define RR_G8_STEP_LO(s, A)                                                                              \
+// (D0, D1) / S2 / S1: the accumulators of this step's chain - even and odd steps run two independent chains, a
+// dependent DMMA every 32 cycles per warp would leave the pipe half idle
+#define RR_G8_STEP_LO(s, A, D0, D1, S2, S1)                                                              \
     "ld.shared.f64 " A ", [wp+" RR_G8_OFF_LO(s) "];\n"                                                   \
-    "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {v0, v1}, {" A "}, {" RR_PB(s) "}, {v0, v1};\n"     \
-    "fma.rn.f64 v2, " A ", " A ", v2;\n add.rn.f64 v3, v3, " A ";\n"
-#define RR_G8_STEP_HI(s, k, A)                                                                           \
+    "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {" D0 ", " D1 "}, {" A "}, {" RR_PB(s) "}, {" D0 ", " D1 "};\n" \
+    "fma.rn.f64 " S2 ", " A ", " A ", " S2 ";\n add.rn.f64 " S1 ", " S1 ", " A ";\n"
+#define RR_G8_STEP_HI(s, k, A, D0, D1, S2, S1)                                                           \
     "ld.shared.f64 " A ", [wq+" RR_G8_OFF_LO(k) "];\n"                                                   \
-    "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {v0, v1}, {" A "}, {" RR_PB(s) "}, {v0, v1};\n"     \
-    "fma.rn.f64 v2, " A ", " A ", v2;\n add.rn.f64 v3, v3, " A ";\n"
+    "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {" D0 ", " D1 "}, {" A "}, {" RR_PB(s) "}, {" D0 ", " D1 "};\n" \
+    "fma.rn.f64 " S2 ", " A ", " A ", " S2 ";\n add.rn.f64 " S1 ", " S1 ", " A ";\n"
 // B fragment of the lanes that own pin j (predicate pq) from a tile column (wp / wq = fragment base of both halves)
 #define RR_G8_PB_LO(s) "@pq ld.shared.f64 " RR_PB(s) ", [wp+" RR_G8_OFF_LO(s) "];\n"
 #define RR_G8_PB_HI(s, k) "@pq ld.shared.f64 " RR_PB(s) ", [wq+" RR_G8_OFF_LO(k) "];\n"
@@ -178,7 +180,7 @@ __device__ __forceinline__ uint32_t rr_core_g8(double &t0, double &t1, double &t
         "{\n"
         ".reg .b32 w0, w1, n0, n1, nz, nw, op, col, x, idx, wp, wq, slo, shi, m0, m1, m2, mw;\n"
         ".reg .f32 fa, fb;\n"
-        ".reg .f64 u0, u1, u2, u3, imm, v0, v1, v2, v3, f0, f1, f2, f3, a0, a1, a2, a3, a4, a5, a6, a7;\n"
+        ".reg .f64 u0, u1, u2, u3, imm, v0, v1, v2, v3, v4, v5, v6, v7, f0, f1, f2, f3, a0, a1, a2, a3, a4, a5, a6, a7;\n"
         ".reg .f64 dr0, dr1, dr2, dr3, dn0, dn1, dn2, dn3, de0, de1, de2, de3, dq0, dq1, dq2, dq3;\n"
         ".reg .b32 ki0, ki1, ki2, ki3;\n"
         ".reg .f64 ta0, ta1, ta2, ta3, tr0, tr1, tr2, tr3, tz0, tz1, tz2, tz3, tm0, tm1, tm2, tm3;\n"
@@ -318,14 +320,17 @@ __device__ __forceinline__ uint32_t rr_core_g8(double &t0, double &t1, double &t
         "ld.shared.v4.b32 {n0, n1, nz, nw}, [%46];\n"
         "mov.f64 v0, 0d0000000000000000;\n mov.f64 v1, 0d0000000000000000;\n"
         "mov.f64 v2, 0d0000000000000000;\n mov.f64 v3, 0d0000000000000000;\n"
-        RR_G8_STEP_LO(0, "a0") RR_G8_STEP_LO(1, "a1") RR_G8_STEP_LO(2, "a2") RR_G8_STEP_LO(3, "a3")
-        RR_G8_STEP_LO(4, "a4") RR_G8_STEP_LO(5, "a5") RR_G8_STEP_LO(6, "a6") RR_G8_STEP_LO(7, "a7")
-        RR_G8_STEP_LO(8, "a0") RR_G8_STEP_LO(9, "a1") RR_G8_STEP_LO(10, "a2") RR_G8_STEP_LO(11, "a3")
-        RR_G8_STEP_LO(12, "a4") RR_G8_STEP_LO(13, "a5") RR_G8_STEP_LO(14, "a6") RR_G8_STEP_LO(15, "a7")
-        RR_G8_STEP_HI(16, 0, "a0") RR_G8_STEP_HI(17, 1, "a1") RR_G8_STEP_HI(18, 2, "a2") RR_G8_STEP_HI(19, 3, "a3")
-        RR_G8_STEP_HI(20, 4, "a4") RR_G8_STEP_HI(21, 5, "a5") RR_G8_STEP_HI(22, 6, "a6") RR_G8_STEP_HI(23, 7, "a7")
-        RR_G8_STEP_HI(24, 8, "a0") RR_G8_STEP_HI(25, 9, "a1") RR_G8_STEP_HI(26, 10, "a2") RR_G8_STEP_HI(27, 11, "a3")
-        RR_G8_STEP_HI(28, 12, "a4") RR_G8_STEP_HI(29, 13, "a5") RR_G8_STEP_HI(30, 14, "a6") RR_G8_STEP_HI(31, 15, "a7")
+        "mov.f64 v4, 0d0000000000000000;\n mov.f64 v5, 0d0000000000000000;\n"
+        "mov.f64 v6, 0d0000000000000000;\n mov.f64 v7, 0d0000000000000000;\n"
+        RR_G8_STEP_LO(0, "a0", "v0", "v1", "v2", "v3") RR_G8_STEP_LO(1, "a1", "v4", "v5", "v6", "v7") RR_G8_STEP_LO(2, "a2", "v0", "v1", "v2", "v3") RR_G8_STEP_LO(3, "a3", "v4", "v5", "v6", "v7")
+        RR_G8_STEP_LO(4, "a4", "v0", "v1", "v2", "v3") RR_G8_STEP_LO(5, "a5", "v4", "v5", "v6", "v7") RR_G8_STEP_LO(6, "a6", "v0", "v1", "v2", "v3") RR_G8_STEP_LO(7, "a7", "v4", "v5", "v6", "v7")
+        RR_G8_STEP_LO(8, "a0", "v0", "v1", "v2", "v3") RR_G8_STEP_LO(9, "a1", "v4", "v5", "v6", "v7") RR_G8_STEP_LO(10, "a2", "v0", "v1", "v2", "v3") RR_G8_STEP_LO(11, "a3", "v4", "v5", "v6", "v7")
+        RR_G8_STEP_LO(12, "a4", "v0", "v1", "v2", "v3") RR_G8_STEP_LO(13, "a5", "v4", "v5", "v6", "v7") RR_G8_STEP_LO(14, "a6", "v0", "v1", "v2", "v3") RR_G8_STEP_LO(15, "a7", "v4", "v5", "v6", "v7")
+        RR_G8_STEP_HI(16, 0, "a0", "v0", "v1", "v2", "v3") RR_G8_STEP_HI(17, 1, "a1", "v4", "v5", "v6", "v7") RR_G8_STEP_HI(18, 2, "a2", "v0", "v1", "v2", "v3") RR_G8_STEP_HI(19, 3, "a3", "v4", "v5", "v6", "v7")
+        RR_G8_STEP_HI(20, 4, "a4", "v0", "v1", "v2", "v3") RR_G8_STEP_HI(21, 5, "a5", "v4", "v5", "v6", "v7") RR_G8_STEP_HI(22, 6, "a6", "v0", "v1", "v2", "v3") RR_G8_STEP_HI(23, 7, "a7", "v4", "v5", "v6", "v7")
+        RR_G8_STEP_HI(24, 8, "a0", "v0", "v1", "v2", "v3") RR_G8_STEP_HI(25, 9, "a1", "v4", "v5", "v6", "v7") RR_G8_STEP_HI(26, 10, "a2", "v0", "v1", "v2", "v3") RR_G8_STEP_HI(27, 11, "a3", "v4", "v5", "v6", "v7")
+        RR_G8_STEP_HI(28, 12, "a4", "v0", "v1", "v2", "v3") RR_G8_STEP_HI(29, 13, "a5", "v4", "v5", "v6", "v7") RR_G8_STEP_HI(30, 14, "a6", "v0", "v1", "v2", "v3") RR_G8_STEP_HI(31, 15, "a7", "v4", "v5", "v6", "v7")
+        "add.rn.f64 v0, v0, v4;\n add.rn.f64 v1, v1, v5;\n add.rn.f64 v2, v2, v6;\n add.rn.f64 v3, v3, v7;\n"
         /* t.t and sum(t) of row g: the four lanes of the row join their quarters */
         "mov.b64 {slo, shi}, v2;\n"
         "shfl.sync.bfly.b32 slo, slo, 1, 31, 0xffffffff;\n shfl.sync.bfly.b32 shi, shi, 1, 31, 0xffffffff;\n"

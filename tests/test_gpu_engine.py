@@ -422,7 +422,9 @@ def test_predict_streams_through_the_engine_and_predict_proba():
         assert np.array_equal(got, got_fm)
         os.environ["RR_B200_PREDICT_CHUNK_BYTES"] = str(8 * d * 70001)
         try:
-            assert np.array_equal(eng.predict(code, consts, X), got)
+            # other chunk boundaries move samples between full tiles (sin / ln fast paths of the PTX core) and the
+            # partial tile at a chunk's end (libdevice): 1-2 ulp per transcendental
+            assert np.allclose(eng.predict(code, consts, X), got, rtol=1e-14, atol=1e-14 * np.abs(want).max())
         finally:
             del os.environ["RR_B200_PREDICT_CHUNK_BYTES"]
         pp = eng.predict_proba(code, consts, X[:50001])
@@ -504,7 +506,7 @@ def test_min_max_nan_operands_on_device():
             r = eng.score(B.Batch.from_exprs(B.MODE_EVAL_ONLY, [[exprs[1]]]))
             want = O.evaluate(O.feature_major(X[keep]), *exprs[1].program())
             ssr = float(((y[keep] - want) ** 2).sum())
-            assert np.isfinite(ssr) and abs(r.ssr[0] - ssr) <= 1e-12 * ssr
+            assert np.isfinite(ssr) and abs(r.ssr[0] - ssr) <= 1e-12 * ssr, (n, r.ssr[0], ssr, int(keep.sum()), np.isnan(want).sum())
 
 
 @pytest.mark.parametrize("delta", [0.0, 1e-7, 1e-5, 1e-3])
