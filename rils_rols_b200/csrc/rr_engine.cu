@@ -519,8 +519,9 @@ int launch_shard(rr_engine *e, rr_engine *s, const rr::SweepPlan &P, const std::
         return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
     // two tile buffers when they fit: the next tile's columns are fetched while this one is interpreted (what an
     // HBM-bound sweep - one small program over many rows - needs; the big neighbourhoods fill the tile and do not care)
-    const bool tile_dbuf = !g8 && 2 * tile_bytes <= cfg.dyn_smem_budget() && env_int("RR_B200_TILE_DBUF", 1) != 0;
-    const size_t smem = g8 ? rr::g8_dyn_smem(std::max(P.max_tile_cols, 1)) : tile_bytes * (tile_dbuf ? 2 : 1) + rr::sweep_ring_smem(NW, cfg.slack);
+    // up to four tile buffers when they fit (an HBM-bound sweep wants several tiles in flight per block)
+    const int tile_dbuf = g8 ? 0 : (int)std::min<size_t>((size_t)std::max(0, env_int("RR_B200_TILE_BUFS", 4) - 1), cfg.dyn_smem_budget() / tile_bytes - 1);
+    const size_t smem = g8 ? rr::g8_dyn_smem(std::max(P.max_tile_cols, 1)) : tile_bytes * (size_t)(tile_dbuf + 1) + rr::sweep_ring_smem(NW, cfg.slack);
     bool special = dd;
     for (const RRIns &x : P.ins)
         if (RR_OP(x.w0) == RI_CLSMET) { special = true; break; }
@@ -573,7 +574,7 @@ int launch_shard(rr_engine *e, rr_engine *s, const rr::SweepPlan &P, const std::
     a.ld_stg = ld_stg;
     a.n_tiles = n_tiles;
     a.dd_ring = env_int("RR_B200_DD_RING", 1);
-    a.tile_dbuf = tile_dbuf ? 1 : 0;
+    a.tile_dbuf = tile_dbuf;
     a.tile_buf_doubles = (int64_t)(tile_bytes / 8);
     if (mark_begin) CU(cudaEventRecord(ev0, s->stream));
     kern<<<dim3(gx, n_chunks), cfg.TH, smem, s->stream>>>(a);

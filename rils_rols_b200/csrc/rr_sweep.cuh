@@ -57,7 +57,7 @@ struct SweepArgs {
     double *stg;            // RI_STG target: column u at stg + u * ld_stg
     int64_t ld_stg;
     int32_t dd_ring;        // double-double plans: 1 = warp reduction through the ring, 0 = shuffle tree
-    int32_t tile_dbuf;      // 1 = two tile buffers of tile_buf_doubles each: the next tile's columns are fetched while this one runs
+    int32_t tile_dbuf;      // tile buffers - 1 (0..3): buffers of tile_buf_doubles each; tiles are fetched that many iterations ahead
     int64_t tile_buf_doubles;
     int32_t n_tiles;        // < 0: probe, the kernel only reports the shared-window address of its dynamic part in acc[0]
 };
@@ -217,11 +217,11 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     constexpr uint32_t HALFB = T * 4u;  // byte offset of the second half of a column
     extern __shared__ __align__(128) unsigned char rr_dyn[];  // [slack][rings: NW x 16 rows x 32 lanes][tile: columns x T]
     __shared__ __align__(16) unsigned char rr_static[kSweepStaticBytes];
-    static_assert(2 * (kInsWindow + 2) * 16 + 4 * 8 <= kSweepStaticBytes, "static shared memory layout");
+    static_assert(2 * (kInsWindow + 2) * 16 + 6 * 8 <= kSweepStaticBytes, "static shared memory layout");
     // each window is followed by its sentinel and one padding slot (the core prefetches one instruction ahead)
     uint4(*ibuf)[kInsWindow + 2] = reinterpret_cast<uint4(*)[kInsWindow + 2]>(rr_static);
     uint64_t *mbar_tile = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16);  // one per tile buffer
-    uint64_t *mbar_ins = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16 + 16);
+    uint64_t *mbar_ins = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16 + 32);
 
     if (a.n_tiles < 0) {
         if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.acc[0] = (double)smem_u32(rr_dyn);
@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     const uint32_t stage_sh = ring_sh + NW * 4096u;          // staging rows: 256 bytes per warp
     double *const rr_tile0 = reinterpret_cast<double *>(rr_dyn + (ring_sh - dyn_sh) + NW * (4096u + 256u));
     const uint32_t tile_sh0 = stage_sh + NW * 256u + tbase;
-    const bool dbuf = a.tile_dbuf != 0;
+    const int nbuf = 1 + a.tile_dbuf;  // 1..4 tile buffers
+    const bool dbuf = nbuf > 1;
     // a program of one window stays in its buffer for the whole launch instead of being fetched again for every tile
     const bool resident_prog = n_win == 1;
     RingCtx rc;
@@ -264,6 +265,8 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
     if (tid == 0) {
         mbar_init(&mbar_tile[0], 1);
         mbar_init(&mbar_tile[1], 1);
+        mbar_init(&mbar_tile[2], 1);
+        mbar_init(&mbar_tile[3], 1);
         mbar_init(&mbar_ins[0], 1);
         mbar_init(&mbar_ins[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         ibuf[1][kInsWindow + 1] = make_uint4(RI_END, 0, 0, 0);
     }
     __syncthreads();
-    uint32_t tile_parity[2] = {0u, 0u}, ins_parity0 = 0, ins_parity1 = 0;
+    uint32_t ins_parity0 = 0, ins_parity1 = 0;
     // warp 0 fetches the staged columns of tile `ti` into tile buffer `bf` (TMA bulk copies on that buffer's mbarrier)
     auto fetch_tile = [&](int ti, int bf) {
         // order this block's earlier generic-proxy accesses to the buffer before the async writes
@@ -294,19 +297,22 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
         }
         mbar_wait(&mbar_ins[0], 0u);
     }
-    if (dbuf && warp == 0 && (int)blockIdx.x < a.n_tiles) fetch_tile(blockIdx.x, 0);
+    if (dbuf && warp == 0)
+        for (int k = 0; k + 1 < nbuf; ++k)
+            if ((int)blockIdx.x + k * (int)gridDim.x < a.n_tiles) fetch_tile((int)blockIdx.x + k * (int)gridDim.x, k);
 
     int it = 0;
     for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x, ++it) {
         const int64_t base = (int64_t)tile_i * T;
-        const int bf = dbuf ? (it & 1) : 0;
+        const int bf = it % nbuf;
         double *const rr_tile = rr_tile0 + (size_t)bf * a.tile_buf_doubles;
         (void)rr_tile;
         const uint32_t tile_sh = tile_sh0 + (uint32_t)bf * (uint32_t)(a.tile_buf_doubles * 8);
         if (warp == 0) {
             if (dbuf) {
-                // the other buffer was last read in the previous iteration, which ended in a block barrier
-                if (tile_i + (int)gridDim.x < a.n_tiles) fetch_tile(tile_i + (int)gridDim.x, bf ^ 1);
+                // the buffer of iteration it + nbuf - 1 was last read in the previous iteration, which ended in a block barrier
+                const int ahead = tile_i + (nbuf - 1) * (int)gridDim.x;
+                if (ahead < a.n_tiles) fetch_tile(ahead, (it + nbuf - 1) % nbuf);
             } else {
                 fetch_tile(tile_i, 0);
             }
@@ -316,8 +322,7 @@ __global__ void __launch_bounds__(TH, (S * TH >= 1024 ? 1 : 2)) rr_sweep_kernel(
                 tma_load_1d(&ibuf[0][0], prog, (uint32_t)(kInsWindow * 16), &mbar_ins[0]);
             }
         }
-        mbar_wait(&mbar_tile[bf], tile_parity[bf]);
-        tile_parity[bf] ^= 1u;
+        mbar_wait(&mbar_tile[bf], (uint32_t)(it / nbuf) & 1u);
 
         const bool partial = base + T > a.n;
         bool valid[S];

@@ -153,18 +153,21 @@ static_assert(RI_OPCOUNT == 158, "update the jump table of rr_core_g8");
 
 // masked stores of a partial tile: samples beyond n are written as zeros (vbits = %45)
 #define RR_G8_MASK4(D0, D1, D2, D3)                                                                      \
-    "and.b32 x, %45, 1;\n setp.ne.u32 q0, x, 0;\n and.b32 x, %45, 2;\n setp.ne.u32 q1, x, 0;\n"         \
-    "and.b32 x, %45, 4;\n setp.ne.u32 q2, x, 0;\n and.b32 x, %45, 8;\n setp.ne.u32 q3, x, 0;\n"         \
+    "and.b32 slo, %45, 1;\n setp.ne.u32 q0, slo, 0;\n and.b32 slo, %45, 2;\n setp.ne.u32 q1, slo, 0;\n" \
+    "and.b32 slo, %45, 4;\n setp.ne.u32 q2, slo, 0;\n and.b32 slo, %45, 8;\n setp.ne.u32 q3, slo, 0;\n" \
     "selp.f64 " D0 ", %0, 0d0000000000000000, q0;\n selp.f64 " D1 ", %1, 0d0000000000000000, q1;\n"      \
     "selp.f64 " D2 ", %2, 0d0000000000000000, q2;\n selp.f64 " D3 ", %3, 0d0000000000000000, q3;\n"
-// store t to the tile column at byte address ADDR (a register): full tiles store t, partial tiles the masked copy
-#define RR_G8_STORE(ADDR, LBL)                                                                            \
-    "setp.eq.u32 p, %45, 15;\n"                                                                          \
-    "@p st.shared.v2.f64 [" ADDR "], {%0, %1};\n @p st.shared.v2.f64 [" ADDR "+2048], {%2, %3};\n"        \
-    "@p bra.uni " LBL ";\n"                                                                                   \
+// store t to the tile column at byte address ADDR (a register). vbits = 15 in every thread of a full tile; a partial
+// tile sets bit 4 in EVERY thread (the branch is block-uniform) and stores the masked copy
+#define RR_G8_STORE(ADDR, LBL)                                                                           \
+    "setp.ne.u32 p, %45, 15;\n"                                                                          \
+    "@p bra.uni " LBL "_P;\n"                                                                            \
+    "st.shared.v2.f64 [" ADDR "], {%0, %1};\n st.shared.v2.f64 [" ADDR "+2048], {%2, %3};\n"
+// the masked variant, reached by the uniform branch above; LBL##_P ... ends in its own dispatch
+#define RR_G8_STORE_PARTIAL(ADDR, LBL)                                                                   \
+    LBL "_P:\n"                                                                                          \
     RR_G8_MASK4("f0", "f1", "f2", "f3")                                                                  \
-    "st.shared.v2.f64 [" ADDR "], {f0, f1};\n st.shared.v2.f64 [" ADDR "+2048], {f2, f3};\n"              \
-    LBL ":\n"
+    "st.shared.v2.f64 [" ADDR "], {f0, f1};\n st.shared.v2.f64 [" ADDR "+2048], {f2, f3};\n"
 
 namespace rr {
 
@@ -215,12 +218,16 @@ __device__ __forceinline__ uint32_t rr_core_g8(double &t0, double &t1, double &t
         "mov.f64 %0, u0;\n mov.f64 %1, u1;\n mov.f64 %2, u2;\n mov.f64 %3, u3;\n"
         RR_DISPATCH
         "L_ST:\n"
-        RR_G8_STORE("col", "ST_FULL_A")
+        RR_G8_STORE("col", "ST_A")
+        RR_DISPATCH
+        RR_G8_STORE_PARTIAL("col", "ST_A")
         RR_DISPATCH
         /* tail of an instruction that carries RR_THEN_ST: store t to the tile column in bits 16-23 of w0 */
         "L_STT:\n"
         "shr.u32 x, w0, 16;\n and.b32 x, x, 255;\n mad.lo.u32 x, x, 4128, " G_TILE ";\n"
-        RR_G8_STORE("x", "ST_FULL_B")
+        RR_G8_STORE("x", "ST_B")
+        RR_DISPATCH
+        RR_G8_STORE_PARTIAL("x", "ST_B")
         RR_DISPATCH
         "L_LDG:\n"
         RR_RELOAD_W1
@@ -282,11 +289,14 @@ __device__ __forceinline__ uint32_t rr_core_g8(double &t0, double &t1, double &t
         "L_MULMST:\n" /* t = t * tile[w1]; tile[lo32(imm)] = t */
         "mov.b64 {slo, shi}, imm;\n mad.lo.u32 idx, slo, 4128, " G_TILE ";\n"
         "mul.rn.f64 %0, %0, u0;\n mul.rn.f64 %1, %1, u1;\n mul.rn.f64 %2, %2, u2;\n mul.rn.f64 %3, %3, u3;\n"
-        RR_G8_STORE("idx", "ST_FULL_C")
+        RR_G8_STORE("idx", "ST_C")
+        RR_DISPATCH
+        RR_G8_STORE_PARTIAL("idx", "ST_C")
         RR_DISPATCH
         /* ---- PINB j: pin j <- tile[w1] as operand register (u0..u3 hold the column) and as reduction partner ---- */
         RR_G8_PINB(0) RR_G8_PINB(1) RR_G8_PINB(2) RR_G8_PINB(3) RR_G8_PINB(4) RR_G8_PINB(5) RR_G8_PINB(6) RR_G8_PINB(7)
         "L_PINB_COMMON:\n"
+        "bar.warp.sync 0xffffffff;\n" /* the column was stored by other lanes of this warp */
         RR_RELOAD_W1
         "sub.u32 x, op, " RR_STR(RR_G8_PINB0_VALUE) ";\n setp.eq.u32 pq, x, " G_G ";\n"
         "mad.lo.u32 wp, w1, 4128, " G_FRAG ";\n add.u32 wq, wp, 2048;\n"
@@ -312,6 +322,7 @@ __device__ __forceinline__ uint32_t rr_core_g8(double &t0, double &t1, double &t
         "L_GRAM8:\n"
         /* the column slot behind this instruction sits in the prefetch registers: this lane's row is byte g & 3 of
            n1 (rows 0-3) or nz (rows 4-7); then the slot is skipped */
+        "bar.warp.sync 0xffffffff;\n" /* the rows were stored by other lanes of this warp */
         "setp.lt.u32 p, " G_G ", 4;\n selp.b32 x, n1, nz, p;\n prmt.b32 x, x, 0, " G_GSEL ";\n"
         "mad.lo.u32 wp, x, 4128, " G_FRAG ";\n add.u32 wq, wp, 2048;\n"
         "ld.shared.b32 m0, [%46+-12];\n"

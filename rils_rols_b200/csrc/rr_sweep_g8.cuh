@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kG8Threads, 2) rr_sweep_g8_kernel(const SweepA
 #pragma unroll
         for (int s = 0; s < 4; ++s)
             if (base + (int64_t)(s >> 1) * (T / 2) + 2 * tid + (s & 1) < a.n) vbits |= 1u << s;
+        if (base + T > a.n) vbits |= 16u;  // partial tile: block-uniform flag for the store handlers
         const double *xg = a.X + base + 2 * tid;                       // this thread's first sample in engine column 0
         const double *xg_frag = a.X + base + (int64_t)warp * 64 + q;   // this lane's first fragment sample
 

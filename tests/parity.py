@@ -108,8 +108,10 @@ def ls_optimum_ssr(A, y) -> float:
     column-normalised design): no correct implementation can report less, whatever it does about rank."""
     nrm = np.linalg.norm(A, axis=0)
     nrm[nrm == 0] = 1.0
-    sol = np.linalg.lstsq(A / nrm, y, rcond=None)[0]
-    r = y - (A / nrm) @ sol
+    # the projection on the WHOLE column space (no singular value is cut off): a truncated least-squares solve would
+    # report the optimum of a smaller space, and a solver that keeps a nearly dependent column can legitimately do better
+    U = np.linalg.svd(A / nrm, full_matrices=False)[0]
+    r = y - U @ (U.T @ y)
     return float(r @ r)
 
 

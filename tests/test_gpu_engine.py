@@ -11,7 +11,8 @@ from tests import parity
 
 pytestmark = pytest.mark.gpu
 
-CFG5_FLOOR = dict(well_posed=0, arbitrary=10**9, sentinel_unconfirmed=10**9)
+# observed (of 4096): 3829 well-posed, 120 rank-deficient drops, 64 ill-conditioned (13 at garbage level on the exact path), 83 sentinels
+CFG5_FLOOR = dict(well_posed=3829, arbitrary=13, sentinel_unconfirmed=0)
 
 
 def ref_dict(z, idx=None):
@@ -501,7 +502,7 @@ def test_min_max_nan_operands_on_device():
             assert only_a.any() and only_b.any()
             assert np.array_equal(mn[only_a], b[only_a]) and np.isnan(mn[only_b]).all()
             # through the reductions: rows whose prediction is NaN poison the residual, the others do not
-            keep = ~np.isnan(O.evaluate(Xfm, *exprs[1].program()))
+            keep = np.isfinite(O.evaluate(Xfm, *exprs[1].program()))
         with Engine(X[keep], y[keep]) as eng:
             r = eng.score(B.Batch.from_exprs(B.MODE_EVAL_ONLY, [[exprs[1]]]))
             want = O.evaluate(O.feature_major(X[keep]), *exprs[1].program())
