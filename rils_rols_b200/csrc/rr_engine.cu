@@ -1284,8 +1284,11 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         size_t off = 0;
         for (size_t i = 0; i < pieces.size(); ++i) {
             Piece &pc = pieces[i];
+            const double tp0 = tnow();
             if (threaded[i]) helpers[i].join();
             else plan_piece(pc);
+            if (verbose) std::fprintf(stderr, "[rr_b200]   piece %zu (%s, %zu cand) plan wait %6.2f ms, %zu ins, %d dots\n", i, pc.g8 ? "g8" : "classic",
+                                      pc.list.size(), tnow() - tp0, pc.P.ins.size(), pc.P.n_dots);
             if (!pc.err.empty()) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, pc.err); }
             pc.off = off;
             if (off + (size_t)pc.P.n_dots > dots_cap) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, "internal: dot vector too small"); }
@@ -1621,6 +1624,9 @@ int score_batch_impl(rr_engine *e, const rr_batch *b, rr_result *res)
     rr::BatchPlanner bp(b, e->d);
     std::string err = bp.analyse((e->flags & RR_FLAG_NO_CSE) != 0);
     if (!err.empty()) return e->fail(RR_ERR_INVALID, "malformed batch: " + err);
+    if (env_int("RR_B200_VERBOSE", 0))
+        std::fprintf(stderr, "[rr_b200] %-28s %8.2f ms\n", "analyse (host)",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
     e->stats.h2d_bytes = e->stats.d2h_bytes = 0;
     e->stats.w_shared = 0.0;
     e->sweep_ms_accum = 0.f;

@@ -106,6 +106,7 @@ enum RRInsOp : uint32_t {
     RI_CDIV_M,    // t = imm / tile[w1]                          (LOAD_C; DIV_M)
     RI_MUL_MM,    // t = tile[w1] * tile[lo32(imm)]              (LOAD_M; MUL_M)
     RI_MUL_M_ST,  // t = t * tile[w1]; tile[lo32(imm)] = t       (MUL_M; ST)
+    RI_MUL_MMM,   // t = (tile[w1] * tile[lo32(imm)]) * tile[hi32(imm)]   (LOAD_M; MUL_M; MUL_M), G8 plans only
     RI_LDPMUL_M0,                             // t = reg[j] * tile[w1]   (LDP j; MUL_M)
     RI_LDPDIV_M0 = RI_LDPMUL_M0 + RR_NREG,    // t = reg[j] / tile[w1]   (LDP j; DIV_M)
     RI_LDMDIVP0 = RI_LDPDIV_M0 + RR_NREG,     // t = tile[w1] / reg[j]   (LOAD_M; USEP j; DIV_M)
@@ -147,7 +148,7 @@ enum : uint32_t {
 RR_HD static inline bool rr_md_fusable(uint32_t op)
 {
     return op == RI_MUL_M || op == RI_DIV_M || op == RI_RDIV_M || op == RI_DIV_C || op == RI_RDIV_C ||
-           (op >= RI_MULP0 && op < RI_FIRST_M) || op == RI_CMUL_M || op == RI_CDIV_M || op == RI_MUL_MM ||
+           (op >= RI_MULP0 && op < RI_FIRST_M) || op == RI_CMUL_M || op == RI_CDIV_M || op == RI_MUL_MM || op == RI_MUL_MMM ||
            (op >= RI_LDPMUL_M0 && op < RI_PINB0);
 }
 #define RR_W0(op, aux) ((uint32_t)(op) | ((uint32_t)(aux) << 8))

@@ -951,14 +951,26 @@ struct BatchPlanner::Chunk {
         } else if (root.op == RR_OP_VAR) {
             col = staged(root.var);  // a bare feature is its own row: nothing to evaluate, nothing to store
         } else {
+            // the slot first: if finding one has to reduce the open group, that RI_GRAM8 goes in FRONT of the term's
+            // code and the term's last operation can carry its store (rr_isa.h RR_THEN_ST)
+            const int32_t sl = alloc_slot(-2);
+            if (!err.empty()) return;
+            slot_rowheld[sl] = 1;
             gen_term(u);
-            const int32_t sl = alloc_slot(keep ? u : -2);
             emit(RI_ST, (uint32_t)sl, 0.0, 0);
+            if (keep) {
+                slot_term[sl] = u;
+                term_loc[u] = (uint32_t)sl;
+            }
             col = (uint32_t)sl;
             free_after = !keep;
         }
         if (!err.empty()) return;
-        if (rows.size() == 8) flush_rows();  // (evaluating u can have flushed already; this is the size guard)
+        if (rows.size() == 8) {
+            // evaluating u has filled the group's last place meanwhile (cannot happen: rows are only added here) - keep
+            // the invariant anyway
+            flush_rows();
+        }
         if (!(col & STAGED)) slot_rowheld[col] = 1;
         GRow r;
         r.col = col;
@@ -1070,6 +1082,13 @@ struct BatchPlanner::Chunk {
                     if (is_reg(op1, RI_USEP0) && op2 == RI_DIV_M) {
                         f.w0 = RI_LDMDIVP0 + (op1 - RI_USEP0);
                         f.w1 = x.w1;
+                        used = 3;
+                    } else if (op1 == RI_MUL_M && op2 == RI_MUL_M && g8) {
+                        // (tile[a] * tile[b]) * tile[c]: b and c ride in the two halves of imm
+                        f.w0 = RI_MUL_MMM;
+                        f.w1 = x.w1;
+                        const uint64_t bits = (uint64_t)P.ins[i + 1].w1 | ((uint64_t)P.ins[i + 2].w1 << 32);
+                        std::memcpy(&f.imm, &bits, 8);
                         used = 3;
                     } else if (op1 == RI_MUL_M) {
                         f.w0 = RI_MUL_MM;

@@ -66,12 +66,12 @@
 #define G_CWORD "%94"
 #define G_CBIT "%95"
 #define G_XGF "%96"
-#define RR_G8_PINB0_VALUE 150
+#define RR_G8_PINB0_VALUE 151
 static_assert(RR_G8_PINB0_VALUE == RI_PINB0, "update RR_G8_PINB0_VALUE");
 
 #define RR_G8_FIRST_M_VALUE 106
 static_assert(RR_G8_FIRST_M_VALUE == RI_FIRST_M, "update RR_G8_FIRST_M_VALUE and the jump table");
-static_assert(RI_OPCOUNT == 158, "update the jump table of rr_core_g8");
+static_assert(RI_OPCOUNT == 159, "update the jump table of rr_core_g8");
 
 #define RR_PB(s) RR_PB_(s)
 #define RR_PB_(s) RR_PBREG_##s
@@ -202,7 +202,7 @@ __device__ __forceinline__ uint32_t rr_core_g8(double &t0, double &t1, double &t
         "L_CMULP0, L_CMULP1, L_CMULP2, L_CMULP3, L_CMULP4, L_CMULP5, L_CMULP6, L_CMULP7, L_CMULP8, L_CMULP9, "
         "L_CDIVP0, L_CDIVP1, L_CDIVP2, L_CDIVP3, L_CDIVP4, L_CDIVP5, L_CDIVP6, L_CDIVP7, L_CDIVP8, L_CDIVP9, "
         "L_LOADM, L_ADDM, L_SUBM, L_RSUBM, L_MULM, L_DIVM, L_RDIVM, L_AXPY, L_OTHER, L_OTHER, "
-        "L_CMULM, L_CDIVM, L_MULMM, L_MULMST, "
+        "L_CMULM, L_CDIVM, L_MULMM, L_MULMST, L_MULMMM, "
         "L_LDPMULM0, L_LDPMULM1, L_LDPMULM2, L_LDPMULM3, L_LDPMULM4, L_LDPMULM5, L_LDPMULM6, L_LDPMULM7, L_LDPMULM8, L_LDPMULM9, "
         "L_LDPDIVM0, L_LDPDIVM1, L_LDPDIVM2, L_LDPDIVM3, L_LDPDIVM4, L_LDPDIVM5, L_LDPDIVM6, L_LDPDIVM7, L_LDPDIVM8, L_LDPDIVM9, "
         "L_LDMDIVP0, L_LDMDIVP1, L_LDMDIVP2, L_LDMDIVP3, L_LDMDIVP4, L_LDMDIVP5, L_LDMDIVP6, L_LDMDIVP7, L_LDMDIVP8, L_LDMDIVP9, "
@@ -285,6 +285,13 @@ __device__ __forceinline__ uint32_t rr_core_g8(double &t0, double &t1, double &t
         "mov.b64 {slo, shi}, imm;\n mad.lo.u32 x, slo, 4128, " G_TILE ";\n"
         "ld.shared.v2.f64 {f0, f1}, [x];\n ld.shared.v2.f64 {f2, f3}, [x+2048];\n"
         "mul.rn.f64 %0, u0, f0;\n mul.rn.f64 %1, u1, f1;\n mul.rn.f64 %2, u2, f2;\n mul.rn.f64 %3, u3, f3;\n"
+        RR_MDCHK RR_DISPATCH
+        "L_MULMMM:\n" /* t = (tile[w1] * tile[lo32(imm)]) * tile[hi32(imm)] */
+        "mov.b64 {slo, shi}, imm;\n mad.lo.u32 x, slo, 4128, " G_TILE ";\n mad.lo.u32 idx, shi, 4128, " G_TILE ";\n"
+        "ld.shared.v2.f64 {f0, f1}, [x];\n ld.shared.v2.f64 {f2, f3}, [x+2048];\n"
+        "ld.shared.v2.f64 {a0, a1}, [idx];\n ld.shared.v2.f64 {a2, a3}, [idx+2048];\n"
+        "mul.rn.f64 %0, u0, f0;\n mul.rn.f64 %1, u1, f1;\n mul.rn.f64 %2, u2, f2;\n mul.rn.f64 %3, u3, f3;\n"
+        "mul.rn.f64 %0, %0, a0;\n mul.rn.f64 %1, %1, a1;\n mul.rn.f64 %2, %2, a2;\n mul.rn.f64 %3, %3, a3;\n"
         RR_MDCHK RR_DISPATCH
         "L_MULMST:\n" /* t = t * tile[w1]; tile[lo32(imm)] = t */
         "mov.b64 {slo, shi}, imm;\n mad.lo.u32 idx, slo, 4128, " G_TILE ";\n"

@@ -30,7 +30,7 @@ RI_CMULP0 = RI_RDIVP0 + RR_NREG
 RI_CDIVP0 = RI_CMULP0 + RR_NREG
 RI_FIRST_M = RI_CDIVP0 + RR_NREG
 (RI_LOAD_M, RI_ADD_M, RI_SUB_M, RI_RSUB_M, RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_AXPY, RI_DOTM,
- RI_DOTMDD, RI_CMUL_M, RI_CDIV_M, RI_MUL_MM, RI_MUL_M_ST, RI_LDPMUL_M0) = range(RI_FIRST_M, RI_FIRST_M + 15)
+ RI_DOTMDD, RI_CMUL_M, RI_CDIV_M, RI_MUL_MM, RI_MUL_M_ST, RI_MUL_MMM, RI_LDPMUL_M0) = range(RI_FIRST_M, RI_FIRST_M + 16)
 RI_LDPDIV_M0 = RI_LDPMUL_M0 + RR_NREG
 RI_LDMDIVP0 = RI_LDPDIV_M0 + RR_NREG
 RI_PINB0 = RI_LDMDIVP0 + RR_NREG
@@ -62,7 +62,7 @@ def ring_rows(aux: int, cnt: int):
 
 
 def md_fusable(op: int) -> bool:
-    return (op in (RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_DIV_C, RI_RDIV_C, RI_CMUL_M, RI_CDIV_M, RI_MUL_MM)
+    return (op in (RI_MUL_M, RI_DIV_M, RI_RDIV_M, RI_DIV_C, RI_RDIV_C, RI_CMUL_M, RI_CDIV_M, RI_MUL_MM, RI_MUL_MMM)
             or RI_MULP0 <= op < RI_FIRST_M or RI_LDPMUL_M0 <= op < RI_PINB0)
 
 
@@ -246,6 +246,10 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                 elif op == RI_MUL_MM:
                     assert col2 < plan.max_tile_cols, f"tile column {col2} out of range"
                     t = src * tile[col2]
+                elif op == RI_MUL_MMM:
+                    col3 = int(plan.ins["imm"][pc - 1:pc].view(np.uint64)[0] >> 32)
+                    assert col2 < plan.max_tile_cols and col3 < plan.max_tile_cols and plan.kind == KIND_GRAM_G8
+                    t = (src * tile[col2]) * tile[col3]
                 elif op == RI_MUL_M_ST:
                     assert col2 < plan.max_tile_cols, f"tile column {col2} out of range"
                     t = t * src
