@@ -11,6 +11,9 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
+#include <numeric>
+#include <random>
 #include <sstream>
 
 #include "rr_search.h"
@@ -183,6 +186,18 @@ py::dict debug_term_batch(py::list trees)
     return d;
 }
 
+// the row order fit() works on: selected[0 .. count) of std::shuffle(iota(n), default_random_engine(seed)),
+// rils_rols_cpp.cpp:774-795 (libstdc++'s shuffle: tests that feed the oracle the same rows need it)
+py::array_t<int32_t> debug_shuffle_index(int n, int seed, int count)
+{
+    std::vector<int> selected(n);
+    std::iota(selected.begin(), selected.end(), 0);
+    std::shuffle(selected.begin(), selected.end(), std::default_random_engine(seed));
+    py::array_t<int32_t> out(std::max(0, std::min(count, n)));
+    std::copy(selected.begin(), selected.begin() + out.size(), out.mutable_data());
+    return out;
+}
+
 std::string debug_to_string(UArr code, DArr consts)
 {
     return rrd::to_string(*rrd::from_postfix(code.data(), code.size(), consts.data(), consts.size()));
@@ -222,5 +237,6 @@ PYBIND11_MODULE(rils_rols_cpp, m)
     m.def("debug_all_candidates", &debug_all_candidates);
     m.def("debug_term_batch", &debug_term_batch);
     m.def("debug_to_string", &debug_to_string);
+    m.def("debug_shuffle_index", &debug_shuffle_index);
     m.def("debug_rebuild", &debug_rebuild);
 }

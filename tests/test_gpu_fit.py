@@ -56,8 +56,10 @@ def test_shadow_replay_of_search_decisions(cfg, classification, max_complexity, 
     rr.fit(X.reshape(-1, 1), y, n, d)
     assert rr.get_fit_calls() in (calls, calls + 1)
     # the driver shuffles the rows with default_random_engine(random_state) before anything else
-    # (rils_rols_cpp.cpp:777-795); sums do not depend on the order beyond rounding, the oracle
-    # gets the unshuffled rows
+    # (rils_rols_cpp.cpp:777-795): the oracle gets the same rows in the same order - rank decisions taken at
+    # rounding level (ColPivHouseholderQR.h:511) depend on the order of summation
+    perm = M.debug_shuffle_index(n, 12345, n)
+    X, y = np.ascontiguousarray(X[perm]), np.ascontiguousarray(y[perm])
     Xfm = O.feature_major(X)
     sst = float(((y - y.mean()) ** 2).sum())
     trace = rr.get_trace()
@@ -69,6 +71,7 @@ def test_shadow_replay_of_search_decisions(cfg, classification, max_complexity, 
         ref = dict(ref_coef=ores.coef, ref_nonzero_pivots=ores.nonzero_pivots, ref_f0=f0, ref_f1=f1, ref_size=fs)
         res = B.Result(tb["coef"] if tb["mode"] == B.MODE_OLS_FIT else np.zeros(1), np.zeros(batch.n_cand, dtype=np.int32),
                        tb["ssr"], np.zeros(batch.n_cand, dtype=np.uint32))
+        # the small configs take the exact path: everything but nonzero_pivots (not traced) is comparable at full strength
         rep = parity.compare(batch, res, ref, Xfm, y, sst, O.evaluate, f"{cfg}/trace", check_nzp=False)
         stats["batches"] += 1
         stats["cands"] += batch.n_cand
