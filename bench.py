@@ -432,7 +432,8 @@ def main():
                                            "distinct_dots", "dot_instances", "sweep_launches", "collectives")},
             "non_sweep_ms_per_step": (wall_ms - sweep_ms) / args.steps,
         }
-        line["roofline"]["hbm_single"] = hbm_single(eng, info, peaks, peak_src)
+        if world == 1:  # (a sharded engine's score() is a collective: rank 0 cannot call it alone)
+            line["roofline"]["hbm_single"] = hbm_single(eng, info, peaks, peak_src)
         if not args.no_parity:
             unsharded = None
             if world > 1:

@@ -951,6 +951,9 @@ int create_sharded(const double *Xsrc, const double *y, int64_t n_src, int32_t d
             pos[(size_t)r] = (int32_t)i;  // a row listed twice keeps its last position (the reference's index is a permutation)
         }
     }
+    const bool verbose = env_int("RR_B200_VERBOSE", 0) != 0;
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    if (verbose) std::fprintf(stderr, "[rr_b200] ingest: index inverted at        %8.2f ms\n", since());
     std::vector<rr_engine *> sh;
     auto bail = [&](int code) {
         for (rr_engine *s : sh) {
@@ -975,6 +978,7 @@ int create_sharded(const double *Xsrc, const double *y, int64_t n_src, int32_t d
         const int rc = create_shard(in, d, G == 1 ? device0 : g, flags & ~(uint32_t)RR_FLAG_X_ROWMAJOR, &s);
         if (rc) return bail(rc);
         sh.push_back(s);
+        if (verbose) std::fprintf(stderr, "[rr_b200] ingest: shard %d resident at         %8.2f ms\n", g, since());
     }
     rr_engine *e = sh[0];
     e->n_object = n_rows;
@@ -1005,6 +1009,7 @@ int create_sharded(const double *Xsrc, const double *y, int64_t n_src, int32_t d
     }
     e->n_total = n_rows;
     e->stats.ingest_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (verbose) std::fprintf(stderr, "[rr_b200] ingest: communicator + target statistics at %8.2f ms\n", since());
     *out = e;
     return RR_OK;
 }

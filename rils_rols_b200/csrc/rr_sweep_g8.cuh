@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kG8Threads, 2) rr_sweep_g8_kernel(const SweepA
 #pragma unroll
         for (int s = 0; s < 4; ++s)
             if (base + (int64_t)(s >> 1) * (T / 2) + 2 * tid + (s & 1) < a.n) vbits |= 1u << s;
-        if (base + T > a.n) vbits |= 16u;  // partial tile: block-uniform flag for the store handlers
+        const bool partial = base + T > a.n;  // block-uniform
         const double *xg = a.X + base + 2 * tid;                       // this thread's first sample in engine column 0
         const double *xg_frag = a.X + base + (int64_t)warp * 64 + q;   // this lane's first fragment sample
 
@@ -118,8 +118,11 @@ __global__ void __launch_bounds__(kG8Threads, 2) rr_sweep_g8_kernel(const SweepA
             for (;;) {
                 uint32_t w0, w1;
                 double imm;
-                const uint32_t code = rr_core_g8(t0, t1, t2, t3, pr, pb, cnt, vbits, ibp, w0, w1, imm, tile_sh, frag_sh, acc_row, gsel, g, q,
-                                                 stage_w, xg, a.ld * 8, stage_s, comb_rd, comb_word, comb_bit, xg_frag);
+                const uint32_t code =
+                    partial ? rr_core_g8_partial(t0, t1, t2, t3, pr, pb, cnt, vbits, ibp, w0, w1, imm, tile_sh, frag_sh, acc_row, gsel, g, q,
+                                                 stage_w, xg, a.ld * 8, stage_s, comb_rd, comb_word, comb_bit, xg_frag)
+                            : rr_core_g8_full(t0, t1, t2, t3, pr, pb, cnt, vbits, ibp, w0, w1, imm, tile_sh, frag_sh, acc_row, gsel, g, q,
+                                              stage_w, xg, a.ld * 8, stage_s, comb_rd, comb_word, comb_bit, xg_frag);
                 if (code == 0) break;
                 if (code == 1) { running = false; break; }
                 // what the core does not implement: libdevice transcendentals outside the fast ranges, rare operators

@@ -14,7 +14,7 @@ import numpy as np
 from .batch import Batch, Result, rr_batch, rr_result
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librr_b200.so")
+LIB_PATH = os.environ.get("RR_B200_LIB") or os.path.join(_HERE, "librr_b200.so")  # (RR_B200_LIB: A/B builds of the kernels)
 _LIB: Optional[C.CDLL] = None
 
 EXPORTS = [
