@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <stdexcept>
@@ -1187,7 +1188,79 @@ int run_exact(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *
 }
 
 // ---- OLS_FIT, Gram path -----------------------------------------------------------------------
-int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *res)
+// A contiguous run of a batch's candidates as a batch of its own (no copy: the candidate offsets are rebased, the term
+// offsets stay absolute into the caller's code array), with its own planner: the pieces of a step are ANALYSED and
+// planned independently, each on its own thread, so that what precedes the first kernel launch is the analysis and
+// the plan of the first, small piece only.
+struct RangeBatch {
+    int32_t c0 = 0, c1 = 0;
+    std::vector<int32_t> ctb;
+    rr_batch view{};
+    std::unique_ptr<rr::BatchPlanner> bp;
+    void init(const rr_batch *b, int32_t lo, int32_t hi, int32_t d)
+    {
+        c0 = lo;
+        c1 = hi;
+        const int32_t t0 = b->cand_term_begin[lo];
+        ctb.resize((size_t)(hi - lo) + 1);
+        for (int32_t c = lo; c <= hi; ++c) ctb[(size_t)(c - lo)] = b->cand_term_begin[c] - t0;
+        view = *b;
+        view.n_cand = hi - lo;
+        view.cand_term_begin = ctb.data();
+        view.term_code_begin = b->term_code_begin + t0;
+        bp.reset(new rr::BatchPlanner(&view, d));
+    }
+};
+// An arbitrary list of a batch's candidates gathered into a batch of its own (the escalation and refinement passes
+// touch a few dozen candidates: they are analysed on their own instead of dragging the whole neighbourhood's analysis)
+struct ListBatch {
+    std::vector<int32_t> cand, ctb, tcb;
+    std::vector<uint32_t> code;
+    rr_batch view{};
+    std::unique_ptr<rr::BatchPlanner> bp;
+    std::string init(const rr_batch *b, const std::vector<int32_t> &list, int32_t d, bool no_cse)
+    {
+        cand = list;
+        ctb.assign(1, 0);
+        tcb.assign(1, 0);
+        code.clear();
+        for (int32_t c : list) {
+            for (int32_t t = b->cand_term_begin[c]; t < b->cand_term_begin[c + 1]; ++t) {
+                code.insert(code.end(), b->code + b->term_code_begin[t], b->code + b->term_code_begin[t + 1]);
+                tcb.push_back((int32_t)code.size());
+            }
+            ctb.push_back((int32_t)tcb.size() - 1);
+        }
+        view = *b;
+        view.n_cand = (int32_t)list.size();
+        view.cand_term_begin = ctb.data();
+        view.term_code_begin = tcb.data();
+        view.code = code.data();
+        view.n_code = (int32_t)code.size();
+        bp.reset(new rr::BatchPlanner(&view, d));
+        return bp->analyse(no_cse);
+    }
+};
+
+// structural validation of an OLS_FIT batch that is going to be analysed piecewise (what BatchPlanner::analyse checks
+// about the offset arrays, without touching the code)
+std::string validate_offsets(const rr_batch *b)
+{
+    if (!b->cand_term_begin || !b->term_code_begin) return "null batch arrays";
+    if (b->cand_term_begin[0] != 0 || b->term_code_begin[0] != 0) return "offset arrays must start at 0";
+    for (int32_t c = 0; c < b->n_cand; ++c)
+        if (b->cand_term_begin[c + 1] < b->cand_term_begin[c]) return "candidate offsets must not decrease";
+    const int32_t n_terms = b->cand_term_begin[b->n_cand];
+    if (n_terms > 0 && !b->code) return "null batch arrays";
+    for (int32_t t = 0; t < n_terms; ++t)
+        if (b->term_code_begin[t + 1] <= b->term_code_begin[t]) return "empty term program";
+    if (b->n_consts < 0 || (b->n_consts > 0 && !b->consts)) return "bad constant pool";
+    if (b->n_code < 0) return "negative code length";
+    if (b->n_code > 0 && n_terms > 0 && b->term_code_begin[n_terms] > b->n_code) return "term offsets exceed the code length";
+    return "";
+}
+
+int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
 {
     const bool verbose = env_int("RR_B200_VERBOSE", 0) != 0;
     auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1202,8 +1275,14 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
 
     const SweepCfg S = choose_cfg(e);
     const int nc = b->n_cand;
+    {
+        const std::string verr = validate_offsets(b);
+        if (!verr.empty()) return e->fail(RR_ERR_INVALID, "malformed batch: " + verr);
+    }
     const int n_terms = b->cand_term_begin[nc];
     const int n_coef = n_terms + nc;
+    const bool no_cse = (e->flags & RR_FLAG_NO_CSE) != 0;
+    auto k_of = [&](int c) { return b->cand_term_begin[c + 1] - b->cand_term_begin[c] + 1; };
     rr::PlanLimits lim = limits_for(e, S, nc);
     rr::ColIds cols{e->d, e->d + 1};
     int rc = ensure_result_buffers(e, nc, n_coef);
@@ -1218,32 +1297,37 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     // DMMA, rr_sweep_g8.cuh); candidates with more terms than there are pins form one classic piece of their own.
     // All pieces write into one dot vector, which is summed over shards / ranks ONCE behind the last piece.
     struct Piece {
-        std::vector<int32_t> list;
-        bool g8 = false;
-        rr::SweepPlan P;
-        std::vector<int32_t> tab, tab_begin;
+        RangeBatch rb;                       // its candidates, analysed on their own
+        std::vector<int32_t> narrow, wide;   // local candidate indices by plan kind
+        rr::SweepPlan P, Pw;                 // the G8 (or classic) plan of `narrow`, the classic plan of `wide`
+        std::vector<int32_t> tab, tab_begin, tabw, tabw_begin;
         std::string err;
-        size_t off = 0;
+        size_t off = 0, offw = 0;
+        bool g8 = false;
     };
-    std::vector<Piece> pieces;
     const bool big_shape = S.S == 4 && S.TH == 128 && lim.target_chunks == 1;
     const bool use_g8 = big_shape && env_int("RR_B200_G8", 1) != 0 && e->d + 3 <= g8_tile_cols();
+    std::vector<Piece> pieces;
     {
+        // piece sizes: a small first piece (its analysis + plan is all that precedes the first launch), the rest in equal
+        // parts; small batches are one piece
         const bool pipelined = env_int("RR_B200_PIPELINE", 1) != 0 && nc >= 1024 && big_shape;
         const int want = pipelined ? std::max(1, env_int("RR_B200_PIECES", 4)) : 1;
-        std::vector<int32_t> main_list, wide;
-        for (int c = 0; c < nc; ++c) (use_g8 && bp.k_of(c) - 1 > RR_NPIN ? wide : main_list).push_back(c);
-        const int np = (int)std::min<size_t>((size_t)want, std::max<size_t>(1, main_list.size() / 256));
-        for (int i = 0; i < np && !main_list.empty(); ++i) {
-            Piece pc;
-            pc.g8 = use_g8;
-            pc.list.assign(main_list.begin() + main_list.size() * i / np, main_list.begin() + main_list.size() * (i + 1) / np);
-            pieces.push_back(std::move(pc));
+        std::vector<int32_t> cut{0};
+        if (want > 1) {
+            const int32_t first = std::min<int32_t>(nc, std::max(128, env_int("RR_B200_FIRST_PIECE", 320)));
+            cut.push_back(first);
+            for (int i = 1; i < want; ++i) cut.push_back(first + (int32_t)((int64_t)(nc - first) * i / (want - 1)));
+        } else {
+            cut.push_back(nc);
         }
-        if (!wide.empty()) {
-            Piece pc;
-            pc.list = std::move(wide);
-            pieces.push_back(std::move(pc));
+        cut.erase(std::unique(cut.begin(), cut.end()), cut.end());
+        pieces.resize(cut.size() - 1);
+        for (size_t i = 0; i + 1 < cut.size(); ++i) {
+            Piece &pc = pieces[i];
+            pc.rb.init(b, cut[i], cut[i + 1], e->d);
+            pc.g8 = use_g8;
+            for (int32_t c = cut[i]; c < cut[i + 1]; ++c) (use_g8 && k_of(c) - 1 > RR_NPIN ? pc.wide : pc.narrow).push_back(c - cut[i]);
         }
     }
     rr::PlanLimits lim_g8 = lim;
@@ -1252,18 +1336,22 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     lim_g8.mdot_rows = false;
     std::string err;
     auto plan_piece = [&](Piece &pc) {
-        pc.err = pc.g8 ? bp.plan_gram_g8(lim_g8, cols, &pc.list, pc.P, pc.tab, pc.tab_begin)
-                       : bp.plan_gram(lim, cols, &pc.list, false, pc.P, pc.tab, pc.tab_begin);
+        pc.err = pc.rb.bp->analyse(no_cse);
+        if (!pc.err.empty()) { pc.err = "malformed batch: " + pc.err; return; }
+        if (!pc.narrow.empty())
+            pc.err = pc.g8 ? pc.rb.bp->plan_gram_g8(lim_g8, cols, &pc.narrow, pc.P, pc.tab, pc.tab_begin)
+                           : pc.rb.bp->plan_gram(lim, cols, &pc.narrow, false, pc.P, pc.tab, pc.tab_begin);
+        if (pc.err.empty() && !pc.wide.empty()) pc.err = pc.rb.bp->plan_gram(lim, cols, &pc.wide, false, pc.Pw, pc.tabw, pc.tabw_begin);
     };
     std::vector<int32_t> tab, tab_begin;
     {
         // the reduced dots of all pieces live in one vector: size it before the first launch
         size_t tab_total = 0;
         for (int c = 0; c < nc; ++c) {
-            const size_t m = (size_t)bp.k_of(c) - 1;
+            const size_t m = (size_t)k_of(c) - 1;
             tab_total += m * (m + 1) / 2 + 2 * m;
         }
-        const size_t dots_cap = tab_total + 64 * pieces.size() + 256;
+        const size_t dots_cap = tab_total + 128 * pieces.size() + 256;
         for (rr_engine *s : shards_of(e)) {
             CU(cudaSetDevice(s->device));
             CU(s->d_dots.ensure(dots_cap * 8));
@@ -1287,36 +1375,50 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
             }
         }
         size_t off = 0;
+        int launches = 0;
         for (size_t i = 0; i < pieces.size(); ++i) {
             Piece &pc = pieces[i];
             const double tp0 = tnow();
             if (threaded[i]) helpers[i].join();
             else plan_piece(pc);
-            if (verbose) std::fprintf(stderr, "[rr_b200]   piece %zu (%s, %zu cand) plan wait %6.2f ms, %zu ins, %d dots\n", i, pc.g8 ? "g8" : "classic",
-                                      pc.list.size(), tnow() - tp0, pc.P.ins.size(), pc.P.n_dots);
+            if (verbose) std::fprintf(stderr, "[rr_b200]   piece %zu (%s, %zu + %zu cand) plan wait %6.2f ms, %zu ins, %d dots\n", i, pc.g8 ? "g8" : "classic",
+                                      pc.narrow.size(), pc.wide.size(), tnow() - tp0, pc.P.ins.size(), pc.P.n_dots);
             if (!pc.err.empty()) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, pc.err); }
-            pc.off = off;
-            if (off + (size_t)pc.P.n_dots > dots_cap) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, "internal: dot vector too small"); }
-            rc = run_sweep(e, pc.P, S, &rr_engine::d_dots, false, nullptr, 0, (int)(i & 1), off, false, pc.g8, false, i == 0);
-            if (rc) { cudaStreamSynchronize(e->stream); return rc; }
-            off += (size_t)round_up(std::max(pc.P.n_dots, 1), 32);
+            for (int w = 0; w < 2; ++w) {
+                const rr::SweepPlan &P = w ? pc.Pw : pc.P;
+                if (P.chunks.empty()) continue;
+                (w ? pc.offw : pc.off) = off;
+                if (off + (size_t)P.n_dots > dots_cap) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, "internal: dot vector too small"); }
+                rc = run_sweep(e, P, S, &rr_engine::d_dots, false, nullptr, 0, launches & 1, off, false, pc.g8 && w == 0, false, launches == 0);
+                if (rc) { cudaStreamSynchronize(e->stream); return rc; }
+                ++launches;
+                off += (size_t)round_up(std::max(P.n_dots, 1), 32);
+            }
+            e->stats.term_instances += pc.rb.bp->n_term_instances();
+            e->stats.distinct_terms += pc.rb.bp->n_terms_distinct();
+            e->stats.w_contract += pc.rb.bp->w_contract();
         }
         if ((rc = reduce_over_ranks(e, &rr_engine::d_dots, 0, off, false))) { cudaStreamSynchronize(e->stream); return rc; }
         // per-candidate tables in candidate order
-        std::vector<std::pair<int32_t, int32_t>> where(nc);
-        for (size_t i = 0; i < pieces.size(); ++i)
-            for (size_t j = 0; j < pieces[i].list.size(); ++j) where[pieces[i].list[j]] = {(int32_t)i, (int32_t)j};
         tab_begin.assign(1, 0);
-        for (int c = 0; c < nc; ++c) {
-            const Piece &pc = pieces[where[c].first];
-            for (int32_t k = pc.tab_begin[where[c].second]; k < pc.tab_begin[where[c].second + 1]; ++k) tab.push_back(pc.tab[k] + (int32_t)pc.off);
-            tab_begin.push_back((int32_t)tab.size());
+        for (size_t i = 0; i < pieces.size(); ++i) {
+            const Piece &pc = pieces[i];
+            std::vector<std::pair<int32_t, int32_t>> where((size_t)(pc.rb.c1 - pc.rb.c0));  // local candidate -> (plan, index in its list)
+            for (size_t j = 0; j < pc.narrow.size(); ++j) where[(size_t)pc.narrow[j]] = {0, (int32_t)j};
+            for (size_t j = 0; j < pc.wide.size(); ++j) where[(size_t)pc.wide[j]] = {1, (int32_t)j};
+            for (size_t lc = 0; lc < where.size(); ++lc) {
+                const bool w = where[lc].first != 0;
+                const std::vector<int32_t> &tb = w ? pc.tabw_begin : pc.tab_begin, &tt = w ? pc.tabw : pc.tab;
+                const size_t base = w ? pc.offw : pc.off;
+                for (int32_t k = tb[(size_t)where[lc].second]; k < tb[(size_t)where[lc].second + 1]; ++k) tab.push_back(tt[(size_t)k] + (int32_t)base);
+                tab_begin.push_back((int32_t)tab.size());
+            }
         }
         CU(cudaStreamSynchronize(e->stream));
-        // the pieces' sweeps as one span: from the first launch (event 2 of the first piece) to the end of the last
-        {
+        // the pieces' sweeps as one span: from the first launch (event 2) to the end of the last
+        if (launches > 0) {
             float ms = 0.f;
-            const int last = (int)((pieces.size() - 1) & 1);
+            const int last = (launches - 1) & 1;
             if (cudaEventElapsedTime(&ms, e->ev[2], e->ev[last ? 5 : 3]) == cudaSuccess) e->sweep_ms_accum += ms;
         }
         phase("plan + sweep gram (pieces)");
@@ -1325,7 +1427,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     // per-candidate solve
     std::vector<int64_t> wsoff(nc + 1, 0);
     for (int c = 0; c < nc; ++c) {
-        const int64_t kk = bp.k_of(c);
+        const int64_t kk = k_of(c);
         wsoff[c + 1] = wsoff[c] + 2 * kk * kk + 10 * kk;
     }
     CU(e->d_ws.ensure((size_t)wsoff[nc] * 8));
@@ -1373,7 +1475,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         std::vector<int64_t> wso(list.size() + 1, 0);
         for (size_t i = 0; i < list.size(); ++i) {
             begin[i] = tab_begin[list[i]];
-            const int64_t kk = bp.k_of(list[i]);
+            const int64_t kk = k_of(list[i]);
             wso[i + 1] = wso[i] + 2 * kk * kk + 10 * kk;
         }
         (void)dd_ws;
@@ -1389,7 +1491,9 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
     if (!escalate.empty()) {
         rr::SweepPlan Pd;
         std::vector<int32_t> dtab, dtab_begin;
-        err = bp.plan_gram(lim, cols, &escalate, true, Pd, dtab, dtab_begin);
+        ListBatch lbd;
+        err = lbd.init(b, escalate, e->d, no_cse);
+        if (err.empty()) err = lbd.bp->plan_gram(lim, cols, nullptr, true, Pd, dtab, dtab_begin);
         if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
         rc = run_sweep(e, Pd, S, &rr_engine::d_rdots, true, nullptr, 0);
         if (rc) return rc;
@@ -1397,7 +1501,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         auto cleanup = [&]() {};
         std::vector<int64_t> wso(escalate.size() + 1, 0);
         for (size_t i = 0; i < escalate.size(); ++i) {
-            const int64_t kk = bp.k_of(escalate[i]);
+            const int64_t kk = k_of(escalate[i]);
             wso[i + 1] = wso[i] + 2 * kk * kk + 10 * kk;
         }
         if ((rc = upload(e, d_dt, dtab.data(), dtab.size())) || (rc = upload(e, d_dtb, dtab_begin.data(), dtab_begin.size())) ||
@@ -1448,7 +1552,19 @@ int run_gram(rr_engine *e, const rr_batch *b, rr::BatchPlanner &bp, rr_result *r
         (void)n_pending_ok;
         rr::SweepPlan Pr;
         std::vector<int32_t> rtab, rtab_begin;
-        err = bp.plan_residual(lim, cols, ok, cs.data(), Pr, rtab, rtab_begin);
+        {
+            // the listed candidates as a batch of their own, their snapped coefficients in that batch's layout
+            ListBatch lbr;
+            err = lbr.init(b, ok, e->d, no_cse);
+            std::vector<double> cs_local((size_t)lbr.ctb.back() + ok.size());
+            std::vector<int32_t> all(ok.size());
+            for (size_t i = 0; i < ok.size(); ++i) {
+                all[i] = (int32_t)i;
+                const int32_t c = ok[i], kk = k_of(c);
+                std::copy(cs.begin() + (b->cand_term_begin[c] + c), cs.begin() + (b->cand_term_begin[c] + c + kk), cs_local.begin() + (lbr.ctb[i] + (int32_t)i));
+            }
+            if (err.empty()) err = lbr.bp->plan_residual(lim, cols, all, cs_local.data(), Pr, rtab, rtab_begin);
+        }
         if (!err.empty()) return e->fail(RR_ERR_INVALID, err);
         rc = run_sweep(e, Pr, S, &rr_engine::d_rdots, false, nullptr, 0);
         if (rc) return rc;
@@ -1626,26 +1742,34 @@ int score_batch_impl(rr_engine *e, const rr_batch *b, rr_result *res)
     CU(cudaSetDevice(e->device));
     // the device clock of the batch starts before the host-side analysis: `last_batch_ms` is what a caller waits for
     CU(cudaEventRecord(e->ev[0], e->stream));
-    rr::BatchPlanner bp(b, e->d);
-    std::string err = bp.analyse((e->flags & RR_FLAG_NO_CSE) != 0);
-    if (!err.empty()) return e->fail(RR_ERR_INVALID, "malformed batch: " + err);
-    if (env_int("RR_B200_VERBOSE", 0))
-        std::fprintf(stderr, "[rr_b200] %-28s %8.2f ms\n", "analyse (host)",
-                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
     e->stats.h2d_bytes = e->stats.d2h_bytes = 0;
     e->stats.w_shared = 0.0;
     e->sweep_ms_accum = 0.f;
-    int rc;
-    if (b->mode == RR_MODE_EVAL_ONLY) {
-        rc = run_eval(e, b, bp, res);
-    } else {
+    bool gram = false;
+    if (b->mode == RR_MODE_OLS_FIT) {
         const bool split = e->rows_split();
         bool exact = !split && e->n_total <= e->exact_max_n;
         if (e->flags & RR_FLAG_FORCE_GRAM) exact = false;
         if ((e->flags & RR_FLAG_FORCE_EXACT) && !split) exact = true;
-        rc = exact ? run_exact(e, b, bp, res) : run_gram(e, b, bp, res);
+        gram = !exact;
     }
-    if (rc) return rc;
+    int rc;
+    const uint64_t ti0 = e->stats.term_instances, dt0 = e->stats.distinct_terms;
+    if (gram) {
+        // the Gram path analyses the batch piece by piece, on the threads that plan the pieces
+        e->stats.w_contract = 0.0;
+        rc = run_gram(e, b, res);
+        if (rc) { e->stats.term_instances = ti0; e->stats.distinct_terms = dt0; return rc; }
+    } else {
+        rr::BatchPlanner bp(b, e->d);
+        std::string err = bp.analyse((e->flags & RR_FLAG_NO_CSE) != 0);
+        if (!err.empty()) return e->fail(RR_ERR_INVALID, "malformed batch: " + err);
+        rc = b->mode == RR_MODE_EVAL_ONLY ? run_eval(e, b, bp, res) : run_exact(e, b, bp, res);
+        if (rc) return rc;
+        e->stats.term_instances += bp.n_term_instances();
+        e->stats.distinct_terms += bp.n_terms_distinct();
+        e->stats.w_contract = bp.w_contract();
+    }
     CU(cudaEventRecord(e->ev[1], e->stream));
     CU(cudaEventSynchronize(e->ev[1]));
     float ms = 0.f;
@@ -1655,12 +1779,9 @@ int score_batch_impl(rr_engine *e, const rr_batch *b, rr_result *res)
     e->stats.last_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     e->stats.batches++;
     e->stats.candidates += b->n_cand;
-    e->stats.term_instances += bp.n_term_instances();
-    e->stats.distinct_terms += bp.n_terms_distinct();
-    e->stats.w_contract = bp.w_contract();
     if (b->mode == RR_MODE_OLS_FIT) {
         for (int c = 0; c < b->n_cand; ++c) {
-            const int64_t k = bp.k_of(c);
+            const int64_t k = b->cand_term_begin[c + 1] - b->cand_term_begin[c] + 1;
             e->stats.dot_instances += k * (k + 1) / 2 + k;
         }
         if (res->flags)

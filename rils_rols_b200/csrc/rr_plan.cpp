@@ -285,7 +285,8 @@ std::string BatchPlanner::analyse(bool no_cse)
     const int32_t n_terms = b_->cand_term_begin[b_->n_cand];
     if (n_terms < 0) return "negative term count";
     if (n_terms > 0 && !b_->code) return "null batch arrays";  // a batch of term-less candidates has no code
-    if (b_->cand_term_begin[0] != 0 || b_->term_code_begin[0] != 0) return "offset arrays must start at 0";
+    // (term offsets are absolute positions in code[]: a contiguous run of a larger batch's candidates is a batch too)
+    if (b_->cand_term_begin[0] != 0 || b_->term_code_begin[0] < 0) return "offset arrays must start at 0";
     for (int32_t c = 0; c < b_->n_cand; ++c)
         if (b_->cand_term_begin[c + 1] < b_->cand_term_begin[c]) return "candidate offsets must not decrease";
     if (b_->n_consts < 0 || (b_->n_consts > 0 && !b_->consts)) return "bad constant pool";
