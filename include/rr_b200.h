@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RR_ABI_VERSION 2
+#define RR_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RR_API __attribute__((visibility("default")))
@@ -179,6 +179,8 @@ typedef struct rr_stats {
     double last_host_ms;       /* last batch: host wall time of rr_score_batch (analyse + planning + waits) */
     double ingest_ms;          /* engine creation: upload + device-side transpose / gather + target statistics */
     uint64_t collectives;      /* NCCL collectives issued by the engine itself (0 with the callback hook) */
+    uint64_t row_groups;       /* ABI 3: groups reduced by the row machine (R8 plans), summed over batches */
+    uint64_t row_group_rows;   /* ABI 3: rows in those groups */
 } rr_stats;
 
 /*

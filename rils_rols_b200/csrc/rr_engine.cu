@@ -33,6 +33,7 @@
 #include "rr_solve.cuh"
 #include "rr_sweep.cuh"
 #include "rr_sweep_g8.cuh"
+#include "rr_sweep_r8.cuh"
 
 namespace {
 
@@ -504,6 +505,13 @@ int g8_tile_cols()
     return (int)((per_block - rr::kG8StageBytes) / rr::kG8ColBytes);
 }
 
+// tile columns an R8 plan may use (rr_sweep_r8.cuh: 256-sample tiles, two blocks per SM)
+int r8_tile_cols()
+{
+    const size_t per_block = kSmemPerSM / rr::kR8BlocksPerSM - kSmemReserved - rr::kR8StaticBytes;
+    return (int)((per_block - rr::kR8StageBytes) / rr::kR8ColBytes);
+}
+
 int launch_shard(rr_engine *e, rr_engine *s, const rr::SweepPlan &P, const std::vector<RRIns> &ins_padded, const SweepCfg &cfg,
                  const XView &view, DotsMember dots, bool dd, double *stg, int64_t ld_stg, int set, size_t dots_off, bool g8 = false,
                  bool mark_begin = true)
@@ -512,26 +520,28 @@ int launch_shard(rr_engine *e, rr_engine *s, const rr::SweepPlan &P, const std::
     DevBuf &d_cols = set ? s->d_cols2 : s->d_cols, &d_acc = set ? s->d_acc2 : s->d_acc;
     cudaEvent_t ev0 = s->ev[set ? 4 : 2], ev1 = s->ev[set ? 5 : 3];
     CU(cudaSetDevice(s->device));
-    const int T = cfg.T();
+    const bool r8 = P.r8;
+    const int T = r8 ? rr::kR8Tile : cfg.T();
     const int NW = cfg.TH / 32;
     const int n_tiles = (int)((view.n + T - 1) / T);
     const size_t tile_bytes = (size_t)std::max(P.max_tile_cols, 1) * T * 8;
-    if (g8 ? P.max_tile_cols > g8_tile_cols() : tile_bytes > cfg.dyn_smem_budget())
+    if (r8 ? P.max_tile_cols > r8_tile_cols() : (g8 ? P.max_tile_cols > g8_tile_cols() : tile_bytes > cfg.dyn_smem_budget()))
         return e->fail(RR_ERR_INVALID, "internal: plan exceeds the shared-memory tile");
     // two tile buffers when they fit: the next tile's columns are fetched while this one is interpreted (what an
     // HBM-bound sweep - one small program over many rows - needs; the big neighbourhoods fill the tile and do not care)
     // up to four tile buffers when they fit (an HBM-bound sweep wants several tiles in flight per block)
-    const int tile_dbuf = g8 ? 0 : (int)std::min<size_t>((size_t)std::max(0, env_int("RR_B200_TILE_BUFS", 4) - 1), cfg.dyn_smem_budget() / tile_bytes - 1);
-    const size_t smem = g8 ? rr::g8_dyn_smem(std::max(P.max_tile_cols, 1)) : tile_bytes * (size_t)(tile_dbuf + 1) + rr::sweep_ring_smem(NW, cfg.slack);
+    const int tile_dbuf = (g8 || r8) ? 0 : (int)std::min<size_t>((size_t)std::max(0, env_int("RR_B200_TILE_BUFS", 4) - 1), cfg.dyn_smem_budget() / tile_bytes - 1);
+    const size_t smem = r8 ? rr::r8_dyn_smem(std::max(P.max_tile_cols, 1)) : g8 ? rr::g8_dyn_smem(std::max(P.max_tile_cols, 1)) : tile_bytes * (size_t)(tile_dbuf + 1) + rr::sweep_ring_smem(NW, cfg.slack);
     bool special = dd;
     for (const RRIns &x : P.ins)
         if (RR_OP(x.w0) == RI_CLSMET) { special = true; break; }
-    SweepKernel kern = g8 ? (SweepKernel)rr::rr_sweep_g8_kernel : sweep_kernel_for(cfg, special);
+    SweepKernel kern = r8 ? (SweepKernel)rr::rr_sweep_r8_kernel : g8 ? (SweepKernel)rr::rr_sweep_g8_kernel : sweep_kernel_for(cfg, special);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            g8 ? (int)rr::g8_dyn_smem(g8_tile_cols()) : (int)(kSmemPerBlockMax - rr::sweep_static_smem())));
+                            r8 ? (int)rr::r8_dyn_smem(r8_tile_cols())
+                               : g8 ? (int)rr::g8_dyn_smem(g8_tile_cols()) : (int)(kSmemPerBlockMax - rr::sweep_static_smem())));
     const int n_chunks = (int)P.chunks.size();
     int gx;
-    if (g8) {
+    if (g8 || r8) {
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cfg.TH, smem);
         gx = std::min(std::max(1, s->sm_count * std::max(1, occ) / std::max(1, n_chunks)), std::max(1, n_tiles));
@@ -578,7 +588,7 @@ int launch_shard(rr_engine *e, rr_engine *s, const rr::SweepPlan &P, const std::
     a.tile_dbuf = tile_dbuf;
     a.tile_buf_doubles = (int64_t)(tile_bytes / 8);
     if (mark_begin) CU(cudaEventRecord(ev0, s->stream));
-    kern<<<dim3(gx, n_chunks), cfg.TH, smem, s->stream>>>(a);
+    kern<<<dim3(gx, n_chunks), r8 ? rr::kR8Threads : cfg.TH, smem, s->stream>>>(a);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ev1, s->stream));
     e->stats.sweep_launches++;
@@ -683,6 +693,10 @@ int run_sweep(rr_engine *e, const rr::SweepPlan &P, const SweepCfg &cfg, DotsMem
     if (rc) return rc;
     if (reduce && P.n_dots > 0 && (rc = reduce_over_ranks(e, dots, dots_off, (size_t)P.n_dots, dd))) return rc;
     e->stats.distinct_dots += P.n_dot_ins;
+    if (P.r8) {
+        e->stats.row_groups += P.n_gram_groups;
+        e->stats.row_group_rows += P.n_gram_rows;
+    }
     e->stats.w_shared += P.w_issued;
     if (!sync) return RR_OK;
     // sweep time is read after the synchronisation
@@ -1334,10 +1348,29 @@ int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
     lim_g8.tile_cols = g8_tile_cols();
     lim_g8.g8 = true;
     lim_g8.mdot_rows = false;
+    // R8 plans (the row machine, rr_sweep_r8.cuh) on request (RR_B200_R8=1): measured slower than G8 plans on the headline
+    // neighbourhood ("the row machine"), so they are not the default. A piece whose rows do not fill their
+    // groups (or that the row machine cannot plan) falls back to its G8 plan.
+    const bool use_r8 = use_g8 && env_int("RR_B200_R8", 0) != 0 && e->d + 4 <= r8_tile_cols();
+    const double r8_min_fill = env_double("RR_B200_R8_MIN_FILL", 3.0);
+    rr::PlanLimits lim_r8 = lim;
+    lim_r8.tile_cols = r8_tile_cols();
     std::string err;
     auto plan_piece = [&](Piece &pc) {
         pc.err = pc.rb.bp->analyse(no_cse);
         if (!pc.err.empty()) { pc.err = "malformed batch: " + pc.err; return; }
+        if (!pc.narrow.empty() && use_r8) {
+            const std::string e8 = pc.rb.bp->plan_gram_r8(lim_r8, cols, &pc.narrow, pc.P, pc.tab, pc.tab_begin);
+            const double work = (double)pc.P.n_gram_groups + (double)pc.P.n_stored_evals;
+            if (e8.empty() && (double)pc.P.n_gram_rows >= r8_min_fill * std::max(work, 1.0)) 
+            {
+                if (!pc.wide.empty()) pc.err = pc.rb.bp->plan_gram(lim, cols, &pc.wide, false, pc.Pw, pc.tabw, pc.tabw_begin);
+                return;
+            }
+            pc.P = rr::SweepPlan();
+            pc.tab.clear();
+            pc.tab_begin.clear();
+        }
         if (!pc.narrow.empty())
             pc.err = pc.g8 ? pc.rb.bp->plan_gram_g8(lim_g8, cols, &pc.narrow, pc.P, pc.tab, pc.tab_begin)
                            : pc.rb.bp->plan_gram(lim, cols, &pc.narrow, false, pc.P, pc.tab, pc.tab_begin);
@@ -1381,7 +1414,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
             const double tp0 = tnow();
             if (threaded[i]) helpers[i].join();
             else plan_piece(pc);
-            if (verbose) std::fprintf(stderr, "[rr_b200]   piece %zu (%s, %zu + %zu cand) plan wait %6.2f ms, %zu ins, %d dots\n", i, pc.g8 ? "g8" : "classic",
+            if (verbose) std::fprintf(stderr, "[rr_b200]   piece %zu (%s, %zu + %zu cand) plan wait %6.2f ms, %zu ins, %d dots\n", i, pc.P.r8 ? "r8" : pc.g8 ? "g8" : "classic",
                                       pc.narrow.size(), pc.wide.size(), tnow() - tp0, pc.P.ins.size(), pc.P.n_dots);
             if (!pc.err.empty()) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, pc.err); }
             for (int w = 0; w < 2; ++w) {
@@ -1389,7 +1422,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
                 if (P.chunks.empty()) continue;
                 (w ? pc.offw : pc.off) = off;
                 if (off + (size_t)P.n_dots > dots_cap) { cudaStreamSynchronize(e->stream); return e->fail(RR_ERR_INVALID, "internal: dot vector too small"); }
-                rc = run_sweep(e, P, S, &rr_engine::d_dots, false, nullptr, 0, launches & 1, off, false, pc.g8 && w == 0, false, launches == 0);
+                rc = run_sweep(e, P, S, &rr_engine::d_dots, false, nullptr, 0, launches & 1, off, false, pc.g8 && w == 0 && !P.r8, false, launches == 0);
                 if (rc) { cudaStreamSynchronize(e->stream); return rc; }
                 ++launches;
                 off += (size_t)round_up(std::max(P.n_dots, 1), 32);

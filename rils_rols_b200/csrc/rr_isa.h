@@ -156,6 +156,55 @@ RR_HD static inline bool rr_md_fusable(uint32_t op)
 #define RR_AUX(w0) ((w0) >> 8)
 #define RR_MDOT_MASK(w0) (((w0) >> 16) & 0xffu)  /* pins to reduce against */
 
+// ---- R8 plans: the row machine (rr_sweep_r8.cuh, BatchPlanner::plan_gram_r8) -------------------------------------
+// A second, independent instruction set for the Gram pass of large-n neighbourhoods. Where the accumulator machine
+// above gives every THREAD four samples and evaluates one term at a time, the row machine gives every LANE one of
+// eight terms ("rows") of the same shape: lane (g, q) = (lane >> 2, lane & 3) of a warp evaluates row g at the
+// samples 4 s + q, s = 0..15, of the warp's 64 samples - which is exactly the A fragment of
+// mma.m8n8k4.f64 (rows x samples), so a freshly evaluated group of rows is reduced against the eight pins (the B
+// fragment, as in G8 plans) straight from registers: no row is ever stored. One dispatched operation works on 16
+// values per lane, so the interpreter's overhead per FP64 operation is a quarter of the accumulator machine's, and
+// eight different rows share it. A block of four warps sweeps tiles of 256 samples, which leaves room for twice as
+// many tile columns (stored sub-expressions) as the 512-sample tiles of the other kernels.
+// Registers per lane: t[16] (accumulator), u[16] (second operand of trees whose two sides both need evaluating),
+// pb[16] (pin g at the lane's 16 samples). Operand modes of LD and the binary operations:
+//   RQ_M  imm = eight tile-column indices, byte g for row g (rows of one group differ in their operands only)
+//   RQ_K  imm = one constant for all rows
+//   RQ_C  one constant per row: four data slots follow, row g's constant at byte 16 + 8 g from the instruction
+//   RQ_U  the register u
+// Shared sub-expressions (and pins) are evaluated once as a "uniform" group - all eight rows identical - and stored
+// to a tile slot with RQ_ST; lanes that read the same column are served by one shared-memory broadcast.
+enum RQOp : uint32_t {
+    RQ_END = 0,      // == RI_END
+    RQ_WINEND = 1,   // == RI_WINEND
+    RQ_NOP = 2,
+    RQ_LD,           // t = operand
+    RQ_ADD, RQ_SUB, RQ_RSUB, RQ_MUL, RQ_DIV, RQ_RDIV,  // t = t op operand / operand op t (R*)
+    RQ_RARE,         // bits 12-15 = RRRareOp, bit 11 = swap (t = operand op t)
+    RQ_SIN, RQ_COS, RQ_LN, RQ_EXP, RQ_SQRT, RQ_SQR,    // t = f(t)
+    RQ_TU,           // u = t
+    RQ_ST,           // tile[byte g of imm] = t
+    // reduce the group in t against the 8 pins, itself and ones (DMMA), bits 16-23 = rows in the group:
+    // w1 = first output id (relative to the chunk's dot_base), imm = wanted bits 0-63, bit 10 g + o of row g
+    // (o = 0..7 pin o, 8 = t.t, 9 = sum t), and a data slot (RQ_NOP) follows whose w1 holds wanted bits 64-79;
+    // the wanted outputs take consecutive ids in bit order
+    RQ_GRAM,
+    // pin (bits 16-23) <- tile column w1 (RQ_PIN_GLOBAL: engine column w1 read from global memory): the lanes
+    // g == pin reload their 16 B-fragment values
+    RQ_PINB,
+    RQ_OPCOUNT
+};
+enum : uint32_t {
+    RQ_M = 0, RQ_K = 1, RQ_U = 2, RQ_C = 3,
+    RQ_MODE_SHIFT = 8,
+    RQ_SWAP = 1u << 11,
+    RQ_RARE_SHIFT = 12,
+    RQ_AUX_SHIFT = 16,
+    RQ_PIN_GLOBAL = 1u << 24,
+};
+#define RQ_W0(op, mode) ((uint32_t)(op) | ((uint32_t)(mode) << RQ_MODE_SHIFT))
+#define RQ_MODE(w0) (((w0) >> RQ_MODE_SHIFT) & 3u)
+
 // One independently schedulable piece of a sweep: its own staged columns, slot state and
 // dot range. Large-n sweeps use one chunk (maximal sharing); small-n sweeps are cut into
 // many chunks so that every SM has work.

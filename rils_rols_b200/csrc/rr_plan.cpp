@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace rr {
@@ -1800,6 +1802,819 @@ std::string BatchPlanner::plan_materialise(const PlanLimits &lim, const ColIds &
 }  // namespace rr
 
 // ---------------------------------------------------------------------------------------------
+// R8 plans: the row machine (rr_isa.h RQ_*, rr_sweep_r8.cuh)
+// ---------------------------------------------------------------------------------------------
+namespace rr {
+namespace {
+
+struct RqOp {
+    uint8_t op, mode, rare;  // rare: RRRareOp | swap << 4
+    int32_t ref;             // RQ_M: >= 0 engine feature column, < 0 stored sub-expression -1 - sid
+    double k;                // RQ_K
+};
+struct RqProg {
+    std::vector<RqOp> ops;
+    std::vector<int32_t> stored;  // distinct stored sub-expressions read, in program order
+    double w = 0.0;               // contract weight of the operations
+    uint64_t shape = 0;           // equal shapes: same operations, modes and constants; operands may differ
+    bool done = false;
+    // programs of stored sub-expressions only: a segment reads at most kSegStored stored operands; between two
+    // segments the value waits in the sub-expression's own slot (so that its operands need not be resident at once)
+    std::vector<uint32_t> seg_begin;
+};
+constexpr int kSegStored = 2;
+
+// Builder of the one chunk of an R8 plan. Terms become ROWS; rows wait in a pool until a pin has to change (or the
+// plan ends), then the pool is sorted by (first stored operand, shape) and cut into groups of up to eight rows of one
+// shape. Sub-expressions with more than one user are STORED: evaluated once as a uniform group, kept in a tile slot
+// (LRU over the slots the tile has left), read by the rows as an RQ_M operand.
+struct R8Builder {
+    const BatchPlanner &bp;
+    const rr_batch *b;
+    SweepPlan &P;
+    DotMap &dots;
+    std::unordered_map<int32_t, int32_t> colmap;
+    int32_t n_staged = 0, slot_cap = 0, slots_used = 0;
+    int32_t pc_begin = 0, dot_base = 0, col_begin = 0;
+    std::string err;
+
+    struct Sub {
+        int32_t term, node;
+        std::vector<int64_t> parents;  // distinct (parent, side) uses, capped
+        int uses = 0;
+        double w = 0.0;  // contract weight of one evaluation
+        mutable double inc_w = -1.0;
+        bool forced = false;
+        int32_t slot = -1;
+        RqProg prog;
+    };
+    CodeTable subs;
+    std::vector<Sub> sub;
+    std::vector<std::vector<int32_t>> node_sid;  // [distinct term][node]; empty until registered
+    std::vector<RqProg> term_prog;
+
+    std::vector<int32_t> slot_sid, slot_lock;
+    std::vector<uint64_t> slot_stamp;
+    uint64_t clock = 1, epoch = 1;
+
+    int32_t pin_term[RR_NPIN];
+    uint64_t pin_stamp[RR_NPIN], pin_hold[RR_NPIN];
+    std::vector<int8_t> term_pin;
+
+    struct Row {
+        int32_t term;
+        uint32_t want;      // bits 0-7 pins, 8 self, 9 one
+        uint64_t key[10];   // dot key of each wanted output
+        int32_t primary;
+        uint64_t shape;
+    };
+    std::vector<Row> pool;
+    uint64_t n_groups = 0, n_rows = 0, n_stored_evals = 0;
+
+    R8Builder(const BatchPlanner &bp_, const rr_batch *b_, SweepPlan &P_, DotMap &dots_, const PlanLimits &lim, const std::vector<int32_t> &cols)
+        : bp(bp_), b(b_), P(P_), dots(dots_), subs(b_, 4096)
+    {
+        pc_begin = (int32_t)P.ins.size();
+        dot_base = P.n_dots;
+        col_begin = (int32_t)P.cols.size();
+        for (int32_t g : cols) {
+            colmap.emplace(g, (int32_t)colmap.size());
+            P.cols.push_back(g);
+        }
+        n_staged = (int32_t)cols.size();
+        slot_cap = std::min(std::min(lim.tile_cols - n_staged, lim.max_slots), 200 - n_staged);
+        node_sid.resize(bp.n_terms_distinct());
+        term_prog.resize(bp.n_terms_distinct());
+        term_pin.assign(bp.n_terms_distinct(), -1);
+        for (int j = 0; j < RR_NPIN; ++j) {
+            pin_term[j] = -1;
+            pin_stamp[j] = pin_hold[j] = 0;
+        }
+    }
+
+    // ---- sub-expression table ----
+    void register_term(int32_t u)
+    {
+        if (!node_sid[u].empty()) return;
+        const Term &T = bp.term(u);
+        const int32_t n = (int32_t)T.nodes.size();
+        std::vector<int32_t> &sid = node_sid[u];
+        sid.assign(n, -1);
+        std::vector<double> wsub(n, 0.0);
+        for (int32_t x = 0; x < n; ++x) {
+            const TermNode &nd = T.nodes[x];
+            if (nd.leaf()) continue;
+            wsub[x] = kW[nd.op] + wsub[nd.left] + (nd.right >= 0 ? wsub[nd.right] : 0.0);
+            const int32_t id = subs.find_or_insert(T.code_begin + nd.first, T.code_begin + x + 1, (int32_t)sub.size());
+            if (id == (int32_t)sub.size()) {
+                Sub s;
+                s.term = u;
+                s.node = x;
+                s.w = wsub[x];
+                sub.push_back(std::move(s));
+            }
+            sid[x] = id;
+        }
+        auto use = [&](int32_t x, int64_t parent) {
+            if (x < 0 || sid[x] < 0) return;
+            Sub &s = sub[sid[x]];
+            if (s.parents.size() >= 16 || std::find(s.parents.begin(), s.parents.end(), parent) != s.parents.end()) return;
+            s.parents.push_back(parent);
+            s.uses = (int)s.parents.size();
+        };
+        // a use = (parent sub-expression, side); the root's parent is the term itself
+        use(n - 1, -(int64_t)(1 + u) * 4);
+        for (int32_t x = 0; x < n; ++x) {
+            const TermNode &nd = T.nodes[x];
+            if (nd.leaf()) continue;
+            use(nd.left, (int64_t)sid[x] * 4 + 1);
+            if (nd.right >= 0) use(nd.right, (int64_t)sid[x] * 4 + 2);
+        }
+    }
+    // Stored: evaluated once per tile as a uniform group and read from a tile slot. Worth it for an expensive
+    // sub-expression with two users, or a cheap one with many (evaluating it inline costs a group the same whether
+    // one row or eight use it).
+    int min_uses_cheap = 6;
+    // contract weight of evaluating sub-expression `sid` when its stored parts are read from their slots
+    double inc_w(int32_t sid) const
+    {
+        const Sub &x = sub[sid];
+        if (x.inc_w >= 0.0) return x.inc_w;
+        const TermNode &nd = bp.term(x.term).nodes[x.node];
+        const std::vector<int32_t> &ids = node_sid[x.term];
+        double w = kW[nd.op];
+        const int32_t kids[2] = {nd.left, nd.right};
+        for (int32_t c : kids)
+            if (c >= 0 && ids[c] >= 0 && !is_stored(ids[c])) w += inc_w(ids[c]);
+        x.inc_w = w;
+        return w;
+    }
+    bool is_stored(int32_t sid) const
+    {
+        if (sid < 0) return false;
+        const Sub &x = sub[sid];
+        return x.forced || (x.uses >= 2 && (x.uses >= min_uses_cheap || inc_w(sid) >= 8.0));
+    }
+
+    // ---- compilation of a tree into a row program ----
+    struct Gen {
+        const Term &T;
+        const std::vector<int32_t> &sid;
+        int32_t top;
+        RqProg &pg;
+        int32_t self = -1;            // stored sub-expression being compiled (segmented), -1 for a row
+        bool u_live = false;
+        std::vector<int32_t> seg_refs;  // stored operands of the open segment
+    };
+    bool simple(const Gen &g, int32_t y) const { return g.T.nodes[y].leaf() || is_stored(g.sid[y]); }
+    bool needs_u(const Gen &g, int32_t y) const
+    {
+        const TermNode &n = g.T.nodes[y];
+        if (simple(g, y)) return false;
+        if (n.right < 0) return needs_u(g, n.left);
+        if (simple(g, n.right)) return needs_u(g, n.left);
+        if (simple(g, n.left)) return needs_u(g, n.right);
+        return true;
+    }
+    void push_op(Gen &g, uint8_t op, uint8_t mode, uint8_t rare, int32_t ref, double k)
+    {
+        RqProg &pg = g.pg;
+        if (op == RQ_TU) g.u_live = true;
+        if (mode == RQ_U && op >= RQ_LD && op <= RQ_RARE) g.u_live = false;
+        if (g.self >= 0 && mode == RQ_M && ref < 0 && op >= RQ_LD && op <= RQ_RARE) {
+            const int32_t s = -1 - ref;
+            if (std::find(g.seg_refs.begin(), g.seg_refs.end(), s) == g.seg_refs.end()) {
+                // a new segment: the value so far waits in the sub-expression's own slot (not while u is live or t is
+                // about to be overwritten: the segment then simply reads one more stored operand)
+                if ((int)g.seg_refs.size() >= kSegStored && !g.u_live && op != RQ_LD) {
+                    pg.seg_begin.push_back((uint32_t)pg.ops.size());
+                    g.seg_refs.clear();
+                    RqOp l;
+                    l.op = RQ_LD;
+                    l.mode = RQ_M;
+                    l.rare = 0;
+                    l.ref = -1 - g.self;
+                    l.k = 0.0;
+                    pg.ops.push_back(l);
+                }
+                g.seg_refs.push_back(s);
+            }
+        }
+        RqOp o;
+        o.op = op;
+        o.mode = mode;
+        o.rare = rare;
+        o.ref = ref;
+        o.k = k;
+        pg.ops.push_back(o);
+        if (mode == RQ_M && ref < 0 && op != RQ_ST) {
+            const int32_t s = -1 - ref;
+            if (s != g.self && std::find(pg.stored.begin(), pg.stored.end(), s) == pg.stored.end()) pg.stored.push_back(s);
+        }
+    }
+    // operand of a binary operation / LD: node y is simple
+    void operand(const Gen &g, int32_t y, uint8_t &mode, int32_t &ref, double &k) const
+    {
+        const TermNode &n = g.T.nodes[y];
+        mode = RQ_M;
+        ref = 0;
+        k = 0.0;
+        if (n.op == RR_OP_CONST) { mode = RQ_K; k = n.cval; }
+        else if (n.op == RR_OP_VAR) ref = n.var;
+        else ref = -1 - g.sid[y];
+    }
+    void bin(Gen &g, uint32_t op, uint8_t mode, int32_t ref, double k, bool swap)
+    {
+        switch (op) {
+        case RR_OP_PLUS: push_op(g, RQ_ADD, mode, 0, ref, k); return;
+        case RR_OP_MULTIPLY: push_op(g, RQ_MUL, mode, 0, ref, k); return;
+        case RR_OP_MINUS: push_op(g, swap ? RQ_RSUB : RQ_SUB, mode, 0, ref, k); return;
+        case RR_OP_DIVIDE: push_op(g, swap ? RQ_RDIV : RQ_DIV, mode, 0, ref, k); return;
+        }
+        uint8_t rare = 0;
+        switch (op) {
+        case RR_OP_POW: rare = RR_POW; break;
+        case RR_OP_LESS_THAN: rare = RR_LT; break;
+        case RR_OP_GREATER_THAN: rare = RR_GT; break;
+        case RR_OP_EQUAL: rare = RR_EQ; break;
+        case RR_OP_NOT_EQUAL: rare = RR_NE; break;
+        case RR_OP_MIN: rare = RR_MIN; break;
+        case RR_OP_MAX: rare = RR_MAX; break;
+        }
+        push_op(g, RQ_RARE, mode, (uint8_t)(rare | (swap ? 16u : 0u)), ref, k);
+    }
+    void gen(Gen &g, int32_t x)  // leaves t = value(node x)
+    {
+        const TermNode &n = g.T.nodes[x];
+        if (n.leaf() || (x != g.top && is_stored(g.sid[x]))) {
+            uint8_t mode;
+            int32_t ref;
+            double k;
+            operand(g, x, mode, ref, k);
+            push_op(g, RQ_LD, mode, 0, ref, k);
+            return;
+        }
+        if (n.right < 0) {
+            gen(g, n.left);
+            uint8_t op = RQ_NOP;
+            switch (n.op) {
+            case RR_OP_SIN: op = RQ_SIN; break;
+            case RR_OP_COS: op = RQ_COS; break;
+            case RR_OP_LN: op = RQ_LN; break;
+            case RR_OP_EXP: op = RQ_EXP; break;
+            case RR_OP_SQRT: op = RQ_SQRT; break;
+            case RR_OP_SQR: op = RQ_SQR; break;
+            default: err = "r8: unknown unary operator"; break;
+            }
+            push_op(g, op, 0, 0, 0, 0.0);
+            g.pg.w += kW[n.op];
+            return;
+        }
+        uint8_t mode;
+        int32_t ref;
+        double k;
+        if (simple(g, n.right)) {
+            gen(g, n.left);
+            operand(g, n.right, mode, ref, k);
+            bin(g, n.op, mode, ref, k, false);
+        } else if (simple(g, n.left)) {
+            gen(g, n.right);
+            operand(g, n.left, mode, ref, k);
+            bin(g, n.op, mode, ref, k, true);
+        } else {
+            const bool ul = needs_u(g, n.left), ur = needs_u(g, n.right);
+            if (ul && ur) {
+                // both sides need the second register: the right one becomes a stored sub-expression
+                sub[g.sid[n.right]].forced = true;
+                gen(g, n.left);
+                operand(g, n.right, mode, ref, k);
+                bin(g, n.op, mode, ref, k, false);
+            } else if (ul) {
+                gen(g, n.left);
+                push_op(g, RQ_TU, 0, 0, 0, 0.0);
+                gen(g, n.right);
+                bin(g, n.op, RQ_U, 0, 0.0, true);  // t = u op t
+            } else {
+                gen(g, n.right);
+                push_op(g, RQ_TU, 0, 0, 0, 0.0);
+                gen(g, n.left);
+                bin(g, n.op, RQ_U, 0, 0.0, false);  // t = t op u
+            }
+        }
+        g.pg.w += kW[n.op];
+    }
+    void finish_prog(RqProg &pg)
+    {
+        uint64_t h = 0x9e3779b97f4a7c15ull;
+        for (const RqOp &o : pg.ops) {
+            uint64_t v = (uint64_t)o.op | ((uint64_t)o.mode << 8) | ((uint64_t)o.rare << 16);
+            h = (h ^ v) * 0xc4ceb9fe1a85ec53ull;
+            h ^= h >> 29;
+        }
+        pg.shape = h;
+        pg.done = true;
+    }
+    const RqProg &row_prog(int32_t u)
+    {
+        RqProg &pg = term_prog[u];
+        if (pg.done) return pg;
+        const Term &T = bp.term(u);
+        const int32_t root = (int32_t)T.nodes.size() - 1;
+        Gen g{T, node_sid[u], -1, pg};  // top = -1: a stored root is read, not re-evaluated
+        gen(g, root);
+        if ((int)pg.stored.size() > kSegStored && err.empty()) {
+            // too many stored operands for a row (a row has no slot to wait in): the whole term becomes a stored
+            // sub-expression and the row reads it
+            sub[node_sid[u][root]].forced = true;
+            pg = RqProg();
+            Gen g2{T, node_sid[u], -1, pg};
+            gen(g2, root);
+        }
+        finish_prog(pg);
+        return pg;
+    }
+    const RqProg &sub_prog(int32_t s)
+    {
+        RqProg &pg = sub[s].prog;
+        if (pg.done) return pg;
+        const Term &T = bp.term(sub[s].term);
+        Gen g{T, node_sid[sub[s].term], sub[s].node, pg};
+        g.self = s;
+        pg.seg_begin.assign(1, 0u);
+        gen(g, sub[s].node);
+        finish_prog(pg);
+        return pg;
+    }
+
+    // ---- emission ----
+    void push(const RRIns &x) { P.ins.push_back(x); }
+    void push_nop()
+    {
+        RRIns x;
+        std::memset(&x, 0, sizeof(x));
+        x.w0 = RQ_NOP;
+        push(x);
+    }
+    uint8_t col_of(int32_t ref)
+    {
+        if (ref >= 0) {
+            auto it = colmap.find(ref);
+            if (it == colmap.end()) { err = "internal: r8 column not staged"; return 0; }
+            return (uint8_t)it->second;
+        }
+        const int32_t sl = sub[-1 - ref].slot;
+        if (sl < 0) { err = "internal: r8 stored operand not resident"; return 0; }
+        return (uint8_t)(n_staged + sl);
+    }
+    // the operations of up to eight programs of one shape, for one half
+    void emit_ops(const RqProg *const *pg, int n, size_t op_begin = 0, size_t op_end = ~(size_t)0)
+    {
+        const size_t n_ops = std::min(pg[0]->ops.size(), op_end);
+        for (size_t i = op_begin; i < n_ops; ++i) {
+            const RqOp &o = pg[0]->ops[i];
+            RRIns x;
+            std::memset(&x, 0, sizeof(x));
+            x.w0 = RQ_W0(o.op, o.mode);
+            if (o.op == RQ_RARE) x.w0 |= ((uint32_t)(o.rare & 15u) << RQ_RARE_SHIFT) | ((o.rare & 16u) ? RQ_SWAP : 0u);
+            const bool has_operand = o.op >= RQ_LD && o.op <= RQ_RARE;
+            if (has_operand && o.mode == RQ_M) {
+                uint8_t c8[8];
+                for (int g = 0; g < 8; ++g) c8[g] = col_of(pg[g < n ? g : 0]->ops[i].ref);
+                std::memcpy(&x.imm, c8, 8);
+            } else if (has_operand && o.mode == RQ_K) {
+                bool same = true;
+                for (int g = 1; g < n; ++g) same = same && std::memcmp(&pg[g]->ops[i].k, &o.k, 8) == 0;
+                if (same) {
+                    x.imm = o.k;
+                } else {
+                    // one constant per row: four data slots behind the instruction, all five in one window
+                    while ((P.ins.size() - (size_t)pc_begin) % RR_INS_WINDOW > RR_INS_WINDOW - 5) push_nop();
+                    x.w0 = RQ_W0(o.op, RQ_C) | (x.w0 & ~0x3ffu);
+                    push(x);
+                    for (int d = 0; d < 4; ++d) {
+                        RRIns c;
+                        double kk[2];
+                        for (int e = 0; e < 2; ++e) {
+                            const int g = 2 * d + e;
+                            kk[e] = pg[g < n ? g : 0]->ops[i].k;
+                        }
+                        std::memcpy(&c, kk, 16);
+                        push(c);
+                    }
+                    continue;
+                }
+            }
+            push(x);
+        }
+    }
+    int32_t alloc_slot()
+    {
+        for (int32_t s = 0; s < slots_used; ++s)
+            if (slot_sid[s] < 0 && slot_lock[s] == 0) return s;
+        if (slots_used < slot_cap) {
+            slot_sid.push_back(-1);
+            slot_lock.push_back(0);
+            slot_stamp.push_back(0);
+            return slots_used++;
+        }
+        int32_t best = -1;
+        for (int32_t s = 0; s < slots_used; ++s)
+            if (slot_lock[s] == 0 && (best < 0 || slot_stamp[s] < slot_stamp[best])) best = s;
+        if (best < 0) { err = "r8: out of tile slots"; return 0; }
+        if (slot_sid[best] >= 0) sub[slot_sid[best]].slot = -1;
+        slot_sid[best] = -1;
+        return best;
+    }
+    // make stored sub-expression s resident (evaluating it as a uniform group when it is not) and lock its slot
+    void ensure_locked(int32_t s)
+    {
+        if (!err.empty()) return;
+        if (sub[s].slot >= 0) {
+            slot_stamp[sub[s].slot] = clock++;
+            slot_lock[sub[s].slot]++;
+            return;
+        }
+        const RqProg &pg = sub_prog(s);
+        if (!err.empty()) return;
+        const RqProg *one[1] = {&pg};
+        int32_t sl = -1;
+        std::vector<int32_t> refs;
+        for (size_t k = 0; k < pg.seg_begin.size() && err.empty(); ++k) {
+            const size_t o0 = pg.seg_begin[k], o1 = k + 1 < pg.seg_begin.size() ? pg.seg_begin[k + 1] : pg.ops.size();
+            refs.clear();
+            for (size_t i = o0; i < o1; ++i) {
+                const RqOp &o = pg.ops[i];
+                if (o.mode == RQ_M && o.ref < 0 && o.op >= RQ_LD && o.op <= RQ_RARE && -1 - o.ref != s &&
+                    std::find(refs.begin(), refs.end(), -1 - o.ref) == refs.end())
+                    refs.push_back(-1 - o.ref);
+            }
+            for (int32_t c : refs) ensure_locked(c);
+            if (!err.empty()) return;
+            if (sl < 0) {
+                sl = alloc_slot();
+                if (!err.empty()) return;
+                sub[s].slot = sl;
+                slot_sid[sl] = s;
+                slot_lock[sl] = 1;
+            }
+            {
+                emit_ops(one, 1, o0, o1);
+                RRIns x;
+                std::memset(&x, 0, sizeof(x));
+                x.w0 = RQ_W0(RQ_ST, RQ_M);
+                uint8_t c8[8];
+                for (int g = 0; g < 8; ++g) c8[g] = (uint8_t)(n_staged + sl);
+                std::memcpy(&x.imm, c8, 8);
+                push(x);
+            }
+            for (int32_t c : refs) slot_lock[sub[c].slot]--;
+        }
+        P.w_issued += pg.w;
+        P.n_term_evals++;
+        n_stored_evals++;
+        slot_stamp[sl] = clock++;
+    }
+    void unlock(int32_t s) { slot_lock[sub[s].slot]--; }
+
+    void emit_group(const Row *rows, int n)
+    {
+        const RqProg *pg[8];
+        std::vector<int32_t> need;
+        for (int g = 0; g < n; ++g) {
+            pg[g] = &term_prog[rows[g].term];
+            for (int32_t s : pg[g]->stored)
+                if (std::find(need.begin(), need.end(), s) == need.end()) need.push_back(s);
+        }
+        for (int32_t s : need) ensure_locked(s);
+        if (!err.empty()) return;
+        uint64_t lo = 0, hi = 0;
+        int n_want = 0;
+        const int32_t id0 = P.n_dots;
+        for (int g = 0; g < n; ++g)
+            for (int o = 0; o < 10; ++o)
+                if ((rows[g].want >> o) & 1u) {
+                    const int bit = g * 10 + o;
+                    if (bit < 64) lo |= 1ull << bit;
+                    else hi |= 1ull << (bit - 64);
+                    dots.set(rows[g].key[o], P.n_dots);
+                    P.n_dots += 1;
+                    P.n_dot_ins += 1;
+                    ++n_want;
+                }
+        {
+            emit_ops(pg, n);
+            RRIns x;
+            std::memset(&x, 0, sizeof(x));
+            x.w0 = RQ_W0(RQ_GRAM, 0) | ((uint32_t)n << RQ_AUX_SHIFT);
+            if ((P.ins.size() - (size_t)pc_begin) % RR_INS_WINDOW == RR_INS_WINDOW - 1) push_nop();
+            x.w1 = (uint32_t)(id0 - dot_base);
+            std::memcpy(&x.imm, &lo, 8);
+            push(x);
+            RRIns d;
+            std::memset(&d, 0, sizeof(d));
+            d.w0 = RQ_NOP;
+            d.w1 = (uint32_t)hi;
+            push(d);
+        }
+        for (int32_t s : need) unlock(s);
+        for (int g = 0; g < n; ++g) P.w_issued += pg[g]->w;
+        P.w_issued += n_want;
+        P.n_term_evals += n;
+        n_groups++;
+        n_rows += n;
+    }
+
+    static bool same_shape(const RqProg &a, const RqProg &b)
+    {
+        if (a.ops.size() != b.ops.size()) return false;
+        for (size_t i = 0; i < a.ops.size(); ++i) {
+            const RqOp &x = a.ops[i], &y = b.ops[i];
+            if (x.op != y.op || x.mode != y.mode || x.rare != y.rare) return false;
+        }
+        return true;
+    }
+    void flush_pool()
+    {
+        if (pool.empty() || !err.empty()) { pool.clear(); return; }
+        const bool shape_first = std::getenv("RR_B200_R8_PRIMARY_FIRST") == nullptr;
+        std::stable_sort(pool.begin(), pool.end(), [shape_first](const Row &a, const Row &b) {
+            if (shape_first) {
+                if (a.shape != b.shape) return a.shape < b.shape;
+                return a.primary < b.primary;
+            }
+            if (a.primary != b.primary) return a.primary < b.primary;
+            return a.shape < b.shape;
+        });
+        const int cap = std::max(1, slot_cap - 4);
+        size_t i = 0;
+        std::vector<int32_t> uni;
+        while (i < pool.size() && err.empty()) {
+            uni = term_prog[pool[i].term].stored;
+            if ((int)uni.size() > cap) { err = "r8: a row reads more stored sub-expressions than the tile has slots"; break; }
+            size_t j = i + 1;
+            while (j < pool.size() && j - i < 8 && pool[j].shape == pool[i].shape &&
+                   same_shape(term_prog[pool[i].term], term_prog[pool[j].term])) {
+                size_t extra = 0;
+                for (int32_t s : term_prog[pool[j].term].stored)
+                    if (std::find(uni.begin(), uni.end(), s) == uni.end()) ++extra;
+                if ((int)(uni.size() + extra) > cap) break;
+                for (int32_t s : term_prog[pool[j].term].stored)
+                    if (std::find(uni.begin(), uni.end(), s) == uni.end()) uni.push_back(s);
+                ++j;
+            }
+            if (std::getenv("RR_B200_R8_DEBUG")) {
+                for (size_t r = i; r < j; ++r) {
+                    const Term &T = bp.term(pool[r].term);
+                    std::vector<std::string> st;
+                    static const char *nm[] = {"?", "c", "x", "+", "-", "*", "/", "sin", "cos", "ln", "exp", "sqrt", "sqr", "pow", "<", ">", "==", "!=", "min", "max"};
+                    for (size_t x = 0; x < T.nodes.size(); ++x) {
+                        const TermNode &nd = T.nodes[x];
+                        char buf[64];
+                        const bool stored_here = !nd.leaf() && is_stored(node_sid[pool[r].term][x]);
+                        std::string v;
+                        if (nd.op == RR_OP_CONST) { std::snprintf(buf, sizeof(buf), "%.4g", nd.cval); v = buf; }
+                        else if (nd.op == RR_OP_VAR) { std::snprintf(buf, sizeof(buf), "x%d", nd.var); v = buf; }
+                        else if (nd.right < 0) { v = std::string(nm[nd.op]) + "(" + st.back() + ")"; st.pop_back(); }
+                        else { std::string rr_ = st.back(); st.pop_back(); std::string ll = st.back(); st.pop_back(); v = "(" + ll + nm[nd.op] + rr_ + ")"; }
+                        if (stored_here) { std::snprintf(buf, sizeof(buf), "[S%d:", node_sid[pool[r].term][x]); v = std::string(buf) + v + "]"; }
+                        st.push_back(v);
+                    }
+                    std::fprintf(stderr, "   row %s\n", st.back().c_str());
+                }
+                std::fprintf(stderr, "group n=%d primary=%d shape=%016llx stored=%zu ops=%zu why=%s\n", (int)(j - i), pool[i].primary,
+                             (unsigned long long)pool[i].shape, uni.size(), term_prog[pool[i].term].ops.size(),
+                             j >= pool.size() ? "end" : (j - i >= 8 ? "full" : (pool[j].shape != pool[i].shape ? "shape" : "slots")));
+            }
+            emit_group(&pool[i], (int)(j - i));
+            i = j;
+        }
+        pool.clear();
+    }
+
+    void add_row(int32_t u, uint32_t want, const uint64_t *key)
+    {
+        const RqProg &pg = row_prog(u);
+        if (!err.empty()) return;
+        Row r;
+        r.term = u;
+        r.want = want;
+        std::memcpy(r.key, key, sizeof(r.key));
+        r.primary = pg.stored.empty() ? -1 : pg.stored[0];
+        r.shape = pg.shape;
+        pool.push_back(r);
+        for (int o = 0; o < 10; ++o)
+            if ((want >> o) & 1u) dots.set(key[o], -2);  // planned; the id follows when the group is emitted
+    }
+
+    void pin_global(int j, int32_t gcol)
+    {
+        RRIns x;
+        std::memset(&x, 0, sizeof(x));
+        x.w0 = RQ_W0(RQ_PINB, 0) | ((uint32_t)j << RQ_AUX_SHIFT) | RQ_PIN_GLOBAL;
+        x.w1 = (uint32_t)gcol;
+        push(x);
+        pin_term[j] = PIN_RESERVED;
+    }
+    void unpin_all() { ++epoch; }
+    int pin_partner(int32_t v)
+    {
+        if (term_pin[v] >= 0) {
+            const int j = term_pin[v];
+            pin_stamp[j] = clock++;
+            pin_hold[j] = epoch;
+            return j;
+        }
+        int j = -1;
+        for (int i = 0; i < RR_NPIN; ++i)
+            if (pin_term[i] == -1) { j = i; break; }
+        if (j < 0) {
+            uint64_t best = ~0ull;
+            for (int i = 0; i < RR_NPIN; ++i)
+                if (pin_term[i] >= 0 && pin_hold[i] != epoch && pin_stamp[i] < best) {
+                    best = pin_stamp[i];
+                    j = i;
+                }
+        }
+        if (j < 0) { err = "internal: no pin available for a reduction partner"; return 0; }
+        if (std::getenv("RR_B200_R8_DEBUG"))
+            std::fprintf(stderr, "pin %d <- term %d (was %d), pool %zu\n", j, v, pin_term[j], pool.size());
+        flush_pool();
+        if (!err.empty()) return 0;
+        const Term &T = bp.term(v);
+        const TermNode &root = T.nodes.back();
+        uint32_t col;
+        int32_t locked = -1;
+        if (root.op == RR_OP_VAR) {
+            col = col_of(root.var);
+        } else if (root.op == RR_OP_CONST) {
+            err = "r8: constant term as a reduction partner";
+            return 0;
+        } else {
+            locked = node_sid[v][T.nodes.size() - 1];
+            ensure_locked(locked);
+            if (!err.empty()) return 0;
+            col = (uint32_t)(n_staged + sub[locked].slot);
+        }
+        RRIns x;
+        std::memset(&x, 0, sizeof(x));
+        x.w0 = RQ_W0(RQ_PINB, 0) | ((uint32_t)j << RQ_AUX_SHIFT);
+        x.w1 = col;
+        push(x);
+        if (locked >= 0) unlock(locked);
+        if (pin_term[j] >= 0) term_pin[pin_term[j]] = -1;
+        pin_term[j] = v;
+        term_pin[v] = (int8_t)j;
+        pin_stamp[j] = clock++;
+        pin_hold[j] = epoch;
+        return j;
+    }
+
+    void close()
+    {
+        flush_pool();
+        RRIns x;
+        std::memset(&x, 0, sizeof(x));
+        x.w0 = RQ_END;
+        push(x);
+        RRChunk c;
+        std::memset(&c, 0, sizeof(c));
+        c.pc_begin = pc_begin;
+        c.n_ins = (int32_t)P.ins.size() - pc_begin;
+        c.dot_base = dot_base;
+        c.n_dots = P.n_dots - dot_base;
+        c.col_begin = col_begin;
+        c.n_cols = n_staged;
+        P.chunks.push_back(c);
+        P.max_tile_cols = std::max(P.max_tile_cols, n_staged + std::max(slots_used, 1));
+        P.n_gram_groups += n_groups;
+        P.n_gram_rows += n_rows;
+        P.n_stored_evals += n_stored_evals;
+        P.r8 = true;
+        if (std::getenv("RR_B200_R8_DEBUG")) {
+            size_t n_st = 0, n_ev = 0;
+            int hist[17] = {0};
+            for (size_t i = 0; i < sub.size(); ++i) {
+                const Sub &x = sub[i];
+                if (is_stored((int32_t)i)) ++n_st;
+                if (x.prog.done) { ++n_ev; hist[std::min(x.uses, 16)]++; }
+            }
+            for (int i = 0; i <= 16; ++i)
+                if (hist[i]) std::fprintf(stderr, "r8:   evaluated stored sub-expressions with %d uses: %d\n", i, hist[i]);
+            std::fprintf(stderr, "r8: %zu sub-expressions, %zu stored, %zu of them evaluated at least once, %llu evaluations, %d slots used\n",
+                         sub.size(), n_st, n_ev, (unsigned long long)n_stored_evals, slots_used);
+        }
+    }
+};
+
+}  // namespace
+
+std::string BatchPlanner::plan_gram_r8(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> *subset, SweepPlan &P,
+                                       std::vector<int32_t> &cand_dot, std::vector<int32_t> &cand_dot_begin) const
+{
+    std::vector<int32_t> list;
+    if (subset) list = *subset;
+    else {
+        list.resize(b_->n_cand);
+        for (int32_t c = 0; c < b_->n_cand; ++c) list[c] = c;
+    }
+    std::vector<Unit> units(list.size());
+    for (size_t i = 0; i < list.size(); ++i) {
+        const int32_t c = list[i];
+        for (int32_t t = b_->cand_term_begin[c]; t < b_->cand_term_begin[c + 1]; ++t)
+            units[i].terms.push_back(term_id_[t]);
+        units[i].w = cand_w_[c];
+        if ((int32_t)units[i].terms.size() > RR_NPIN) return "candidate too wide for an R8 plan";
+    }
+    std::vector<ChunkSpec> specs;
+    std::vector<int32_t> always;
+    PlanLimits one = lim;
+    one.target_chunks = 1;
+    std::string err = cut_chunks(*this, units, one, always, 3, specs);
+    if (!err.empty()) return err;
+    if (specs.size() != 1) return "r8: the neighbourhood does not fit one chunk";
+
+    cand_dot.clear();
+    cand_dot_begin.assign(1, 0);
+    DotMap dots((size_t)units.size() * 8 + 64);
+    const int64_t KEY_YC = -1, KEY_ONE = -2;
+    auto key = [](int64_t a, int64_t b) -> uint64_t {
+        if (a > b) std::swap(a, b);
+        return ((uint64_t)(uint32_t)(int32_t)a << 32) | (uint64_t)(uint32_t)(int32_t)b;
+    };
+    R8Builder ch(*this, b_, P, dots, lim, specs[0].cols);
+    if (ch.slot_cap < 3) return "r8: tile too small";
+    for (const Unit &u : units)
+        for (int32_t t : u.terms) ch.register_term(t);
+    ch.pin_global(0, cols.yc);  // pin 0 = the centred target, for the whole chunk
+    auto missing = [&](int64_t a, int64_t b) { return dots.find(key(a, b)) == nullptr; };
+    std::vector<int32_t> N, done;
+    for (size_t ui = 0; ui < units.size(); ++ui) {
+        const std::vector<int32_t> &T = units[ui].terms;
+        const int32_t m = (int32_t)T.size();
+        N.clear();
+        for (int32_t i = 0; i < m; ++i) {
+            bool miss = missing(T[i], KEY_YC) || missing(T[i], KEY_ONE);
+            for (int32_t j = 0; j < m && !miss; ++j) miss = missing(T[i], T[j]);
+            if (miss && std::find(N.begin(), N.end(), T[i]) == N.end()) N.push_back(T[i]);
+        }
+        // pinned terms first: what is new in this candidate then meets all of its partners in its one row
+        // ... then terms whose own reductions exist already (they only lack pairs with what is new here: as partners
+        // they are pinned once for the whole family of candidates that share them), the new terms last
+        std::stable_partition(N.begin(), N.end(), [&](int32_t u) { return !missing(u, u); });
+        std::stable_partition(N.begin(), N.end(), [&](int32_t u) { return ch.term_pin[u] >= 0; });
+        ch.unpin_all();
+        done.clear();
+        for (size_t q = 0; q < N.size(); ++q) {
+            const int32_t u = N[q];
+            const bool self = missing(u, u), one_ = missing(u, KEY_ONE), with_yc = missing(u, KEY_YC);
+            bool any = self || one_ || with_yc;
+            for (int32_t v : done)
+                if (v != u && missing(u, v)) { any = true; break; }
+            if (!any) { done.push_back(u); continue; }
+            uint32_t want = with_yc ? 1u : 0u;
+            uint64_t k10[10] = {0};
+            if (with_yc) k10[0] = key(u, KEY_YC);
+            for (int32_t v : done) {
+                if (v == u || !missing(u, v)) continue;
+                const int j = ch.pin_partner(v);
+                if (!ch.err.empty()) return ch.err;
+                if ((want >> j) & 1u) return "internal: duplicate pinned partner";
+                want |= 1u << j;
+                k10[j] = key(u, v);
+            }
+            if (self) { want |= 1u << 8; k10[8] = key(u, u); }
+            if (one_) { want |= 1u << 9; k10[9] = key(u, KEY_ONE); }
+            ch.add_row(u, want, k10);
+            if (!ch.err.empty()) return ch.err;
+            done.push_back(u);
+        }
+    }
+    ch.close();
+    if (!ch.err.empty()) return ch.err;
+    for (size_t ui = 0; ui < units.size(); ++ui) {
+        const std::vector<int32_t> &T = units[ui].terms;
+        const int32_t m = (int32_t)T.size();
+        auto put = [&](uint64_t k) -> bool {
+            const int32_t *it = dots.find(k);
+            if (!it || *it < 0) return false;
+            cand_dot.push_back(*it);
+            return true;
+        };
+        for (int32_t i = 0; i < m; ++i)
+            for (int32_t j = i; j < m; ++j)
+                if (!put(key(T[i], T[j]))) return "internal: missing Gram dot";
+        for (int32_t i = 0; i < m; ++i)
+            if (!put(key(T[i], KEY_YC))) return "internal: missing Gram dot";
+        for (int32_t i = 0; i < m; ++i)
+            if (!put(key(T[i], KEY_ONE))) return "internal: missing Gram dot";
+        cand_dot_begin.push_back((int32_t)cand_dot.size());
+    }
+    return "";
+}
+
+}  // namespace rr
+
+// ---------------------------------------------------------------------------------------------
 // host-only tooling entry points (include/rr_b200.h)
 // ---------------------------------------------------------------------------------------------
 #include <cstdlib>
@@ -1851,6 +2666,7 @@ extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kin
             lim.g8 = true;
             err = bp.plan_gram_g8(lim, cols, nullptr, P, tab, tab_begin);
             break;
+        case 7: err = bp.plan_gram_r8(lim, cols, nullptr, P, tab, tab_begin); break;
         default: err = "bad kind";
         }
     }

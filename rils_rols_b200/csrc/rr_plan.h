@@ -55,6 +55,8 @@ struct SweepPlan {
     uint64_t n_term_evals = 0;
     uint64_t n_dot_ins = 0;
     uint64_t n_gram_groups = 0, n_gram_rows = 0;  // G8 plans: RI_GRAM8 instructions and the rows they reduce
+    bool r8 = false;  // an R8 plan (rr_isa.h RQ_*): runs in rr_sweep_r8_kernel only
+    uint64_t n_stored_evals = 0;  // R8 plans: evaluations of stored sub-expressions
     bool empty() const { return chunks.empty(); }
 };
 
@@ -104,6 +106,11 @@ public:
     // the same for a G8 plan (candidates of at most RR_NPIN terms)
     std::string plan_gram_g8(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> *subset, SweepPlan &out,
                              std::vector<int32_t> &cand_dot, std::vector<int32_t> &cand_dot_begin);
+
+    // the same for an R8 plan (rr_isa.h: the row machine); fails with a message when the neighbourhood does not fit
+    // one chunk or a tree needs more tile slots than there are - the caller then plans a G8 piece instead
+    std::string plan_gram_r8(const PlanLimits &lim, const ColIds &cols, const std::vector<int32_t> *subset, SweepPlan &out,
+                             std::vector<int32_t> &cand_dot, std::vector<int32_t> &cand_dot_begin) const;
 
     // explicit residual of the model sum_i cs_i t_i + cs_free (snapped coefficients, reference
     // association order) for the listed candidates: per candidate 1 (r.r) + m (r.t_i) + 1 (r.1) ids.

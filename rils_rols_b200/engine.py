@@ -24,7 +24,7 @@ EXPORTS = [
     "rr_predict_proba_rowmajor", "rr_feature_r2", "rr_engine_read_rows", "rr_measure_fp64_peak",
     "rr_debug_plan_batch", "rr_debug_plan_free", "rr_debug_plan_concurrency_check",
 ]
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class EngineError(RuntimeError):
@@ -44,7 +44,8 @@ class rr_stats(C.Structure):
                 ("distinct_dots", C.c_uint64), ("dot_instances", C.c_uint64), ("last_sweep_ms", C.c_double),
                 ("last_batch_ms", C.c_double), ("w_contract", C.c_double), ("w_shared", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("last_host_ms", C.c_double),
-                ("ingest_ms", C.c_double), ("collectives", C.c_uint64)]
+                ("ingest_ms", C.c_double), ("collectives", C.c_uint64), ("row_groups", C.c_uint64),
+                ("row_group_rows", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -70,7 +70,7 @@ INS_DT = np.dtype([("w0", "<u4"), ("w1", "<u4"), ("imm", "<f8")])
 CHUNK_DT = np.dtype([("pc_begin", "<i4"), ("n_ins", "<i4"), ("dot_base", "<i4"), ("n_dots", "<i4"),
                      ("col_begin", "<i4"), ("n_cols", "<i4"), ("r0", "<i4"), ("r1", "<i4")])
 
-KIND_GRAM, KIND_GRAM_DD, KIND_EVAL, KIND_EVAL_METRICS, KIND_MATERIALISE, KIND_RESIDUAL, KIND_GRAM_G8 = range(7)
+KIND_GRAM, KIND_GRAM_DD, KIND_EVAL, KIND_EVAL_METRICS, KIND_MATERIALISE, KIND_RESIDUAL, KIND_GRAM_G8, KIND_GRAM_R8 = range(8)
 
 
 class rr_debug_plan(C.Structure):
@@ -337,6 +337,143 @@ def run(plan: Plan, cols_global: np.ndarray, n_stg: int = 0):
                     rows_expected, ring_cnt = ring_rows(aux, ring_cnt)
             assert out == int(ch["dot_base"]) + int(ch["n_dots"]), "chunk dot count mismatch"
     return dots[: plan.n_dots], stg
+
+
+# ---- R8 plans: the row machine (rr_isa.h RQ_*) ----
+(RQ_END, RQ_WINEND, RQ_NOP, RQ_LD, RQ_ADD, RQ_SUB, RQ_RSUB, RQ_MUL, RQ_DIV, RQ_RDIV, RQ_RARE, RQ_SIN, RQ_COS, RQ_LN,
+ RQ_EXP, RQ_SQRT, RQ_SQR, RQ_TU, RQ_ST, RQ_GRAM, RQ_PINB, RQ_OPCOUNT) = range(22)
+RQ_M, RQ_K, RQ_U, RQ_C = 0, 1, 2, 3
+RQ_SWAP, RQ_PIN_GLOBAL = 1 << 11, 1 << 24
+
+
+def run_r8(plan: Plan, cols_global: np.ndarray):
+    """Emulates an R8 plan: eight rows of one shape per group. Returns (dots[n_dots], stats dict)."""
+    assert plan.kind == KIND_GRAM_R8
+    n = cols_global.shape[1]
+    dots = np.zeros(max(plan.n_dots, 1))
+    m = np.ones(n, dtype=bool)
+    stats = dict(groups=0, rows=0, stores=0, pinb=0, ops=0)
+    with np.errstate(all="ignore"):
+        for ch in plan.chunks:
+            ncols = int(ch["n_cols"])
+            tile = {i: cols_global[plan.cols[ch["col_begin"] + i]].copy() for i in range(ncols)}
+            t = np.zeros((8, n))
+            u = np.zeros((8, n))
+            pins = [None] * RR_NPIN
+            D = np.zeros((8, 10))
+            pc = int(ch["pc_begin"])
+            end = pc + int(ch["n_ins"])
+            base = int(ch["dot_base"])
+            n_out = 0
+            ended = False
+            while pc < end:
+                w0, w1 = int(plan.ins["w0"][pc]), int(plan.ins["w1"][pc])
+                imm = float(plan.ins["imm"][pc])
+                immbits = int(plan.ins["imm"][pc:pc + 1].view(np.uint64)[0])
+                c8 = list(plan.ins[pc:pc + 1].view(np.uint8)[8:16])
+                pc += 1
+                op, mode = w0 & 0xFF, (w0 >> 8) & 3
+                if op == RQ_END:
+                    ended = True
+                    break
+                if op == RQ_NOP:
+                    continue
+                stats["ops"] += 1
+                b = None
+                if RQ_LD <= op <= RQ_RARE:
+                    if mode == RQ_M:
+                        for c in c8:
+                            assert c < plan.max_tile_cols and c in tile, f"tile column {c} not available"
+                        b = np.stack([tile[c] for c in c8])
+                    elif mode == RQ_K:
+                        b = np.full((8, n), imm)
+                    elif mode == RQ_C:
+                        assert (pc - 1 - int(ch["pc_begin"])) % RR_INS_WINDOW <= RR_INS_WINDOW - 5, "constants straddle a window"
+                        k8 = plan.ins[pc:pc + 4].view(np.float64)
+                        assert k8.shape == (8,)
+                        pc += 4
+                        b = np.repeat(k8[:, None], n, axis=1)
+                    else:
+                        assert mode == RQ_U
+                        b = u
+                if op == RQ_LD: t[:, m] = b[:, m]
+                elif op == RQ_ADD: t[:, m] = (t + b)[:, m]
+                elif op == RQ_SUB: t[:, m] = (t - b)[:, m]
+                elif op == RQ_RSUB: t[:, m] = (b - t)[:, m]
+                elif op == RQ_MUL: t[:, m] = (t * b)[:, m]
+                elif op == RQ_DIV: t[:, m] = (t / b)[:, m]
+                elif op == RQ_RDIV: t[:, m] = (b / t)[:, m]
+                elif op == RQ_RARE:
+                    x, v = (b, t) if w0 & RQ_SWAP else (t, b)
+                    r = (w0 >> 12) & 0xF
+                    if r == RR_POW: res = np.power(x, v)
+                    elif r == RR_LT: res = (x < v).astype(float)
+                    elif r == RR_GT: res = (x > v).astype(float)
+                    elif r == RR_EQ: res = (x == v).astype(float)
+                    elif r == RR_NE: res = (x != v).astype(float)
+                    elif r == RR_MIN: res = np.where(x < v, x, v)
+                    else: res = np.where(x > v, x, v)
+                    t[:, m] = res[:, m]
+                elif op == RQ_SIN: t[:, m] = np.sin(t[:, m])
+                elif op == RQ_COS: t[:, m] = np.cos(t[:, m])
+                elif op == RQ_LN: t[:, m] = np.log(t[:, m])
+                elif op == RQ_EXP: t[:, m] = np.exp(t[:, m])
+                elif op == RQ_SQRT: t[:, m] = np.sqrt(t[:, m])
+                elif op == RQ_SQR: t[:, m] = (t * t)[:, m]
+                elif op == RQ_TU: u[:, m] = t[:, m]
+                elif op == RQ_ST:
+                    assert mode == RQ_M
+                    for g in range(8):
+                        c = c8[g]
+                        assert ncols <= c < plan.max_tile_cols, f"store to tile column {c}"
+                        if c not in tile:
+                            tile[c] = np.zeros(n)
+                        tile[c][m] = t[g, m]
+                    stats["stores"] += 1
+                elif op == RQ_PINB:
+                    j = (w0 >> 16) & 0xFF
+                    assert j < RR_NPIN
+                    if w0 & RQ_PIN_GLOBAL:
+                        pins[j] = cols_global[w1].copy()
+                    else:
+                        assert w1 in tile, f"PINB from tile column {w1}"
+                        pins[j] = tile[w1].copy()
+                    stats["pinb"] += 1
+                elif op == RQ_GRAM:
+                    n_rows = (w0 >> 16) & 0xFF
+                    assert 1 <= n_rows <= 8
+                    for g in range(n_rows):
+                        a = t[g, m]
+                        for o in range(8):
+                            if pins[o] is not None:
+                                D[g, o] += float(np.dot(a, pins[o][m]))
+                        D[g, 8] += float(np.dot(a, a))
+                        D[g, 9] += float(np.sum(a))
+                    if True:
+                        assert (pc - 1 - int(ch["pc_begin"])) % RR_INS_WINDOW != RR_INS_WINDOW - 1, "GRAM at a window end"
+                        d0 = int(plan.ins["w0"][pc])
+                        assert (d0 & 0xFF) == RQ_NOP, "GRAM without its data slot"
+                        bits = immbits | (int(plan.ins["w1"][pc]) << 64)
+                        pc += 1
+                        assert bits >> (10 * n_rows) == 0, "wanted bits beyond the last row"
+                        out = base + w1
+                        assert w1 == n_out, "group outputs are not consecutive"
+                        for g in range(n_rows):
+                            for o in range(10):
+                                if bits >> (10 * g + o) & 1:
+                                    if o < 8:
+                                        assert pins[o] is not None, "GRAM against an empty pin"
+                                    dots[out] += D[g, o]
+                                    out += 1
+                        n_out = out - base
+                        D[:] = 0.0
+                        stats["groups"] += 1
+                        stats["rows"] += n_rows
+                else:
+                    raise AssertionError(f"bad R8 opcode {op}")
+            assert ended, "chunk without END"
+            assert n_out == int(ch["n_dots"]), "chunk dot count mismatch"
+    return dots[: plan.n_dots], stats
 
 
 def engine_columns(X_rowmajor: np.ndarray, y: np.ndarray) -> np.ndarray:

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     L = E.lib()
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/rr_b200.h but not exported"
-    assert L.rr_abi_version() == E.ABI_VERSION == 2 and set(names) == set(E.EXPORTS)
+    assert L.rr_abi_version() == E.ABI_VERSION == 3 and set(names) == set(E.EXPORTS)
 
 
 def test_no_cpu_fallback():
@@ -422,6 +422,73 @@ def test_g8_plan_reproduces_design_matrix_products(golden, cfg, prefix, tile_col
             assert okb.all(), f"cand {c}"
     print(f"\n{cfg} tile_cols={tc}: {len(plan.ins)} instructions (classic {len(classic.ins)}), {groups} GRAM8 with {rows} rows "
           f"({rows / groups:.2f} per group), w_issued {plan.w_issued:.0f} (classic {classic.w_issued:.0f})")
+
+
+@pytest.mark.parametrize("slots", [32, 10])
+@pytest.mark.parametrize("cfg,prefix", [("cfg1_toy", "ls3_"), ("cfg3_breast_cancer", "ls0_"), ("cfg5", "")])
+def test_r8_plan_reproduces_design_matrix_products(golden, cfg, prefix, slots):
+    """R8 plans (rr_isa.h RQ_*: the row machine - eight rows of one shape per group, evaluated in the DMMA fragment
+    layout and reduced straight from registers): every Gram / A^T yc / column-sum entry the solver reads must be the
+    design-matrix product, with plenty of tile slots for the stored sub-expressions and with very few; the distinct
+    reductions are the classic plan's."""
+    if cfg == "cfg5":
+        from rils_rols_b200 import workloads as W
+
+        full = W.cfg5_neighbourhood()
+        X, y = W.cfg5_data(300)
+    else:
+        z = golden(cfg)
+        X, y = z["X"], z["y"]
+        full = B.Batch.load_fields(z, prefix)
+    batch = full.subset(narrow_subset(full, 500))
+    d = X.shape[1]
+    tc = slots + d  # the engine's tile has 52 columns (rr_sweep_r8.cuh)
+    plan = EMU.Plan(batch, d, EMU.KIND_GRAM_R8, tile_cols=tc)
+    classic = EMU.Plan(batch, d, EMU.KIND_GRAM, tile_cols=56)
+    assert plan.max_tile_cols <= tc
+    assert plan.n_dots == classic.n_dots
+    G_cols = EMU.engine_columns(X, y)
+    dots, st = EMU.run_r8(plan, G_cols)
+    assert st["groups"] >= 1 and st["rows"] >= st["groups"]
+    Xfm = O.feature_major(X)
+    yc = y - y.mean()
+    with np.errstate(all="ignore"):
+        for c in range(0, batch.n_cand, 5):
+            A = design(Xfm, batch, c)
+            G, byc = gram_from_dots(plan, dots, batch, c, X.shape[0])
+            want = A.T @ A
+            ok = np.isclose(G, want, rtol=1e-12, atol=0, equal_nan=True) | (~np.isfinite(want) & ~np.isfinite(G))
+            assert ok.all(), f"cand {c}"
+            wb = A[:, :-1].T @ yc
+            okb = np.isclose(byc, wb, rtol=1e-10, atol=1e-9 * np.abs(yc).sum(), equal_nan=True) | (~np.isfinite(wb) & ~np.isfinite(byc))
+            assert okb.all(), f"cand {c}"
+    print(f"\n{cfg} tile columns {tc}: {len(plan.ins)} instruction slots, {st['groups']} groups with {st['rows']} rows "
+          f"({st['rows'] / st['groups']:.2f} per group), {st['stores']} stores, {st['pinb']} pin loads, "
+          f"w_issued {plan.w_issued:.0f} (classic {classic.w_issued:.0f})")
+
+
+def test_r8_plan_two_register_trees_and_forced_stores():
+    """Trees whose two sides both need evaluating use the second register; when both sides need it themselves, one side
+    becomes a stored sub-expression."""
+    v = B.Expr.var
+    a = (B.sin(v(0)) + v(1)) * (B.exp(v(1)) - v(2))                      # t / u
+    b = ((B.sin(v(0)) + v(1)) * (B.cos(v(1)) - v(2))) / ((B.sqrt(v(2)) + 1.5) * (B.ln(v(0)) - v(1)))  # forced store
+    c = 2.5 / (v(0) - B.sqrt(v(1) / v(2)))
+    cands = [[a, v(0)], [b, v(1) * v(2)], [c, a], [b, c, a]]
+    batch = B.Batch.from_exprs(B.MODE_OLS_FIT, cands)
+    rng = np.random.default_rng(1)
+    X = rng.uniform(0.5, 2.5, size=(300, 3))
+    y = rng.normal(size=300)
+    plan = EMU.Plan(batch, 3, EMU.KIND_GRAM_R8, tile_cols=10)
+    ops = plan.ins["w0"] & 0xFF
+    assert (ops == EMU.RQ_TU).any() and (ops == EMU.RQ_ST).any()
+    dots, st = EMU.run_r8(plan, EMU.engine_columns(X, y))
+    Xfm = O.feature_major(X)
+    for ci in range(batch.n_cand):
+        A = design(Xfm, batch, ci)
+        G, byc = gram_from_dots(plan, dots, batch, ci, X.shape[0])
+        assert np.allclose(G, A.T @ A, rtol=1e-12, atol=0)
+        assert np.allclose(byc, A[:, :-1].T @ (y - y.mean()), rtol=1e-9, atol=1e-9 * np.abs(y).sum())
 
 
 def test_g8_plan_rejects_wide_candidates():

@@ -574,3 +574,46 @@ def test_config4_golden_neighbourhoods(golden):
 # observed (752 candidates of the three recorded neighbourhoods): 704 well-posed (16 of them under the kappa * sqrt(n) bound),
 # 43 ill-conditioned - none at garbage level -, 5 sentinels
 CFG4_FLOOR = dict(well_posed=704, arbitrary=0)
+
+
+def test_row_machine_matches_the_accumulator_machine_and_the_oracle(golden, monkeypatch):
+    """R8 plans (rr_sweep_r8.cuh: eight rows of one shape per warp, evaluated in the DMMA fragment layout) against G8
+    plans of the same neighbourhood and against the C oracle, at a size with a partial last tile. The two kernels
+    share no device code on the Gram pass; the solve ladder behind them is the same."""
+    z = golden("cfg5_neighbourhood")
+    n = (1 << 18) + 133  # more 512-row tiles than resident blocks (the large-n plan shapes), and a partial last tile
+    X, y = workloads.cfg5_data(n)
+    batch = B.Batch.load_fields(z)
+    with Engine(X, y) as eng:
+        monkeypatch.setenv("RR_B200_R8", "1")
+        monkeypatch.setenv("RR_B200_R8_MIN_FILL", "0")
+        res_r = eng.score(batch)
+        st_r = eng.stats()
+        assert st_r["row_groups"] > 0 and st_r["row_group_rows"] >= 4 * st_r["row_groups"], st_r
+        again = eng.score(batch)
+        assert np.array_equal(res_r.ssr.view(np.uint64), again.ssr.view(np.uint64))  # bit-deterministic
+        monkeypatch.setenv("RR_B200_R8", "0")
+        res_g = eng.score(batch)
+        st_g = eng.stats()
+        assert st_g["row_groups"] == 2 * st_r["row_groups"]  # the third call planned no R8 piece
+        sst = eng.info().sst
+    fin_r, fin_g = np.isfinite(res_r.ssr), np.isfinite(res_g.ssr)
+    assert np.array_equal(fin_r, fin_g)
+    plain = fin_r & ((res_r.flags | res_g.flags) & (B.RES_RANKDEF | B.RES_DD) == 0)
+    assert plain.sum() >= 3500
+    err = np.abs(res_r.ssr[plain] - res_g.ssr[plain]) / (np.abs(res_g.ssr[plain]) + 1e-12 * sst)
+    assert err.max() <= 1e-9, (err.max(), int(np.argmax(err)))
+    # a subset against the oracle
+    idx = list(range(0, 4096, 41))
+    sub = batch.subset(idx)
+    Xfm = O.feature_major(X)
+    ref, _ = oracle_ref(Xfm, y, sub)
+    with Engine(X, y) as eng:
+        monkeypatch.setenv("RR_B200_R8", "1")
+        monkeypatch.setenv("RR_B200_R8_MIN_FILL", "0")
+        res = eng.score(sub)
+        assert eng.stats()["row_groups"] > 0
+        rep = parity.compare(sub, res, ref, Xfm, y, eng.info().sst, O.evaluate, "cfg5/r8/subset", check_nzp=False)
+    assert rep["well_posed"] >= 80, rep
+    print(f"\nR8 vs G8 at n = {n}: max relative SSR difference {err.max():.2e} over {int(plain.sum())} candidates; "
+          f"{st_r['row_groups']} groups, {st_r['row_group_rows'] / st_r['row_groups']:.2f} rows per group; vs oracle: {rep}")
