@@ -1326,15 +1326,30 @@ int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
         // piece sizes: a small first piece (its analysis + plan is all that precedes the first launch), the rest in equal
         // parts; small batches are one piece
         const bool pipelined = env_int("RR_B200_PIPELINE", 1) != 0 && nc >= 1024 && big_shape;
-        // fewer pieces share more (measured at 2^24 rows on one GPU: 3 pieces 200.9 ms, 4: 203.5, 6: 210.5 per step, one piece
-        // 194 ms of sweeps behind 7 ms of planning); shorter sweeps (rows sharded over several GPUs) hide less planning per
-        // piece and get one piece more
-        const int want = pipelined ? std::max(1, env_int("RR_B200_PIECES", e->n >= (1 << 23) ? 3 : 4)) : 1;
+        // Pieces are planned on their own threads from the start, so piece k's plan exists after ~1.6 us per candidate
+        // of it and is needed when the sweeps of the pieces before it end (~2.9e-6 us per candidate and row of this
+        // shard). Fewer, larger pieces share more (2^24 rows on one GPU: two pieces 199 ms per step, four 203.5, six
+        // 210.5; one piece: 194 ms of sweeps behind 7 ms of planning), so every piece is made as large as the sweeps in
+        // front of it can hide: 128 + the rest at 2^24 rows, 128 + ~600 + ~2900 + the rest at 2^21 rows per GPU.
+        // RR_B200_PIECES = k forces the old shape (a first piece, then k - 1 equal parts).
+        const int forced = env_int("RR_B200_PIECES", 0);
         std::vector<int32_t> cut{0};
-        if (want > 1) {
+        if (pipelined && forced != 1) {
             const int32_t first = std::min<int32_t>(nc, std::max(64, env_int("RR_B200_FIRST_PIECE", 128)));
             cut.push_back(first);
-            for (int i = 1; i < want; ++i) cut.push_back(first + (int32_t)((int64_t)(nc - first) * i / (want - 1)));
+            if (forced > 1) {
+                for (int i = 1; i < forced; ++i) cut.push_back(first + (int32_t)((int64_t)(nc - first) * i / (forced - 1)));
+            } else {
+                const double t_sweep = env_double("RR_B200_SWEEP_US_PER_CAND_ROW", 2.9e-6) * (double)e->n;
+                const double t_plan = env_double("RR_B200_PLAN_US_PER_CAND", 1.6);
+                int32_t cum = first;
+                while (cum < nc) {
+                    int32_t next = (int32_t)std::min<double>((double)(nc - cum), std::max(256.0, (200.0 + t_sweep * cum) / t_plan));
+                    if (nc - cum - next < 128) next = nc - cum;
+                    cum += next;
+                    cut.push_back(cum);
+                }
+            }
         } else {
             cut.push_back(nc);
         }

@@ -1523,6 +1523,7 @@ std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols
         return ((uint64_t)(uint32_t)(int32_t)a << 32) | (uint64_t)(uint32_t)(int32_t)b;
     };
     std::vector<int32_t> ids;
+    int32_t prev_m = 0, prev_T[RR_NPIN], prev_pid[RR_NPIN][RR_NPIN + 2];
     for (const ChunkSpec &cs : specs) {
         Chunk ch(*this, P, lim, cs.cols, RR_NPIN);
         ch.g8 = true;
@@ -1530,11 +1531,56 @@ std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols
         for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
             const std::vector<int32_t> &T = units[ui].terms;
             const int32_t m = (int32_t)T.size();
-            auto missing = [&](int64_t a, int64_t b) { return dots.find(key(a, b)) == nullptr; };
+            // every pair of this candidate is looked up ONCE: pid[i][j] (i <= j < m: Gram, j = m: with yc, j = m + 1:
+            // with ones) holds the reduction id or -1; the rows added below fill in what was missing
+            // (neighbours differ in one or two terms: what the previous candidate found is taken from its table)
+            int32_t pid[RR_NPIN][RR_NPIN + 2];
+            int32_t was[RR_NPIN];
+            for (int32_t i = 0; i < m; ++i) {
+                was[i] = -1;
+                for (int32_t k = 0; k < prev_m; ++k)
+                    if (prev_T[k] == T[i]) { was[i] = k; break; }
+            }
+            for (int32_t i = 0; i < m; ++i) {
+                for (int32_t j = i; j < m; ++j) {
+                    int32_t id = -1;
+                    if (was[i] >= 0 && was[j] >= 0) id = was[i] <= was[j] ? prev_pid[was[i]][was[j]] : prev_pid[was[j]][was[i]];
+                    if (id < 0) {
+                        const int32_t *it = dots.find(key(T[i], T[j]));
+                        id = it ? *it : -1;
+                    }
+                    pid[i][j] = id;
+                }
+                int32_t idy = was[i] >= 0 ? prev_pid[was[i]][prev_m] : -1, ido = was[i] >= 0 ? prev_pid[was[i]][prev_m + 1] : -1;
+                if (idy < 0) {
+                    const int32_t *iy = dots.find(key(T[i], KEY_YC));
+                    idy = iy ? *iy : -1;
+                }
+                if (ido < 0) {
+                    const int32_t *io = dots.find(key(T[i], KEY_ONE));
+                    ido = io ? *io : -1;
+                }
+                pid[i][m] = idy;
+                pid[i][m + 1] = ido;
+            }
+            auto index_of = [&](int64_t t) -> int32_t {
+                for (int32_t i = 0; i < m; ++i)
+                    if (T[i] == t) return i;
+                return -1;
+            };
+            auto slot = [&](int64_t a, int64_t b) -> int32_t & {
+                // a is a term of this candidate; b a term, KEY_YC or KEY_ONE
+                const int32_t i = index_of(a);
+                if (b == KEY_YC) return pid[i][m];
+                if (b == KEY_ONE) return pid[i][m + 1];
+                const int32_t j = index_of(b);
+                return i <= j ? pid[i][j] : pid[j][i];
+            };
+            auto missing = [&](int64_t a, int64_t b) { return slot(a, b) < 0; };
             std::vector<int32_t> N;
             for (int32_t i = 0; i < m; ++i) {
-                bool miss = missing(T[i], KEY_YC) || missing(T[i], KEY_ONE);
-                for (int32_t j = 0; j < m && !miss; ++j) miss = missing(T[i], T[j]);
+                bool miss = pid[i][m] < 0 || pid[i][m + 1] < 0;
+                for (int32_t j = 0; j < m && !miss; ++j) miss = (i <= j ? pid[i][j] : pid[j][i]) < 0;
                 if (miss && std::find(N.begin(), N.end(), T[i]) == N.end()) N.push_back(T[i]);
             }
             // resident terms first: what is new in this candidate then meets all of its partners in its one row
@@ -1556,6 +1602,7 @@ std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols
                 }
                 uint32_t pin_mask = with_yc ? 1u : 0u;
                 uint64_t pin_key[RR_NPIN];
+                int64_t pin_partner_term[RR_NPIN];
                 if (with_yc) pin_key[0] = key(u, KEY_YC);
                 for (int32_t v : done) {
                     if (v == u || !missing(u, v)) continue;
@@ -1564,6 +1611,7 @@ std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols
                     if ((pin_mask >> j) & 1u) return "internal: duplicate pinned partner";
                     pin_mask |= 1u << j;
                     pin_key[j] = key(u, v);
+                    pin_partner_term[j] = v;
                 }
                 bool transient = false;
                 if (q + 1 == N.size() && lim.transient_horizon > 0) {
@@ -1576,28 +1624,45 @@ std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols
                 if (!ch.err.empty()) return ch.err;
                 size_t k = 0;
                 for (int j = 0; j < RR_NPIN; ++j)
-                    if ((pin_mask >> j) & 1u) dots.set(pin_key[j], ids[k++]);
-                if (self) dots.set(key(u, u), ids[k++]);
-                if (one) dots.set(key(u, KEY_ONE), ids[k++]);
+                    if ((pin_mask >> j) & 1u) {
+                        dots.set(pin_key[j], ids[k]);
+                        if (j > 0) slot(u, pin_partner_term[j]) = ids[k];
+                        else pid[index_of(u)][m] = ids[k];
+                        ++k;
+                    }
+                if (self) {
+                    dots.set(key(u, u), ids[k]);
+                    slot(u, u) = ids[k++];
+                }
+                if (one) {
+                    dots.set(key(u, KEY_ONE), ids[k]);
+                    pid[index_of(u)][m + 1] = ids[k++];
+                }
                 done.push_back(u);
             }
-            for (int32_t i = 0; i < m; ++i)
-                for (int32_t j = i; j < m; ++j) {
-                    const int32_t *it = dots.find(key(T[i], T[j]));
-                    if (!it) return "internal: missing Gram dot";
-                    cand_dot.push_back(*it);
+            // (a term listed twice by one candidate shares its ids through the map, not through pid)
+            auto take = [&](int32_t have, uint64_t k) -> bool {
+                if (have < 0) {
+                    const int32_t *it = dots.find(k);
+                    if (!it) return false;
+                    have = *it;
                 }
-            for (int32_t i = 0; i < m; ++i) {
-                const int32_t *it = dots.find(key(T[i], KEY_YC));
-                if (!it) return "internal: missing Gram dot";
-                cand_dot.push_back(*it);
-            }
-            for (int32_t i = 0; i < m; ++i) {
-                const int32_t *it = dots.find(key(T[i], KEY_ONE));
-                if (!it) return "internal: missing Gram dot";
-                cand_dot.push_back(*it);
-            }
+                cand_dot.push_back(have);
+                return true;
+            };
+            for (int32_t i = 0; i < m; ++i)
+                for (int32_t j = i; j < m; ++j)
+                    if (!take(pid[i][j], key(T[i], T[j]))) return "internal: missing Gram dot";
+            for (int32_t i = 0; i < m; ++i)
+                if (!take(pid[i][m], key(T[i], KEY_YC))) return "internal: missing Gram dot";
+            for (int32_t i = 0; i < m; ++i)
+                if (!take(pid[i][m + 1], key(T[i], KEY_ONE))) return "internal: missing Gram dot";
             cand_dot_begin.push_back((int32_t)cand_dot.size());
+            prev_m = m;
+            for (int32_t i = 0; i < m; ++i) {
+                prev_T[i] = T[i];
+                for (int32_t j = i; j < m + 2; ++j) prev_pid[i][j] = j < m ? pid[i][j] : pid[i][j];
+            }
         }
         if (!ch.err.empty()) return ch.err;
         ch.close();
@@ -2617,6 +2682,7 @@ std::string BatchPlanner::plan_gram_r8(const PlanLimits &lim, const ColIds &cols
 // ---------------------------------------------------------------------------------------------
 // host-only tooling entry points (include/rr_b200.h)
 // ---------------------------------------------------------------------------------------------
+#include <chrono>
 #include <cstdlib>
 #include <thread>
 
@@ -2636,7 +2702,18 @@ extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kin
     if (!batch || !out) return RR_ERR_INVALID;
     std::memset(out, 0, sizeof(*out));
     rr::BatchPlanner bp(batch, d);
+    const auto tm0 = std::chrono::steady_clock::now();
     std::string err = bp.analyse(no_cse != 0);
+    const auto tm1 = std::chrono::steady_clock::now();
+    struct Rep {
+        std::chrono::steady_clock::time_point a, b;
+        ~Rep()
+        {
+            if (std::getenv("RR_B200_PLAN_TIMING"))
+                std::fprintf(stderr, "analyse %.3f ms, plan %.3f ms\n", std::chrono::duration<double, std::milli>(b - a).count(),
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b).count());
+        }
+    } rep{tm0, tm1};
     rr::SweepPlan P;
     std::vector<int32_t> tab, tab_begin;
     if (err.empty()) {
