@@ -191,12 +191,17 @@ def fit_leg(calls: int, with_reference: bool):
     for name, cls, mc, ncalls in (("cfg1_toy", False, 50, calls), ("cfg2_diabetes", False, 20, calls),
                                   ("cfg3_breast_cancer", True, 20, calls), ("cfg4_1Mx10", False, 50, calls)):
         X, y = workloads.cfg4_data(1_000_000, 10) if name.startswith("cfg4") else workloads.config_data(name)
-        rr = M.rils_rols(cls, ncalls, 100000, 0.001, mc, 1.0, False, 12345)
-        t = time.perf_counter()
-        rr.fit(X.reshape(-1, 1), y, X.shape[0], X.shape[1])
-        wall = time.perf_counter() - t
+        # two runs, the faster one reported (a fit of configs 1-3 is a second of host work: one descheduled thread
+        # doubles it; observed 0.57 / 0.61 / 1.21 s for three runs of config 2 on one box); both walls are recorded
+        walls = []
+        for _ in range(2):
+            rr = M.rils_rols(cls, ncalls, 100000, 0.001, mc, 1.0, False, 12345)
+            t = time.perf_counter()
+            rr.fit(X.reshape(-1, 1), y, X.shape[0], X.shape[1])
+            walls.append(time.perf_counter() - t)
+        wall = min(walls)
         rec = {"n": int(X.shape[0]), "d": int(X.shape[1]), "fit_calls": int(rr.get_fit_calls()), "fit_wall_s": wall,
-               "total_time_s": rr.get_total_time(), "model": rr.get_model_string()}
+               "fit_wall_s_runs": walls, "total_time_s": rr.get_total_time(), "model": rr.get_model_string()}
         if R is not None:
             rcalls = ncalls if not name.startswith("cfg4") else 120
             ref = R.rils_rols(cls, rcalls, 100000, 0.001, mc, 1.0, False, 12345)
