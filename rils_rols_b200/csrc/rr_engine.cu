@@ -319,7 +319,7 @@ struct rr_engine {
     // grow-only work buffers
     DevBuf d_ins2, d_chunks2, d_cols2, d_acc2;  // second sweep in flight (run_gram plans the batch in two halves)
     DevBuf d_ins, d_chunks, d_cols, d_acc, d_dots, d_rdots, d_tab, d_rtab, d_ws, d_wsoff, d_list, d_coef, d_cs,
-        d_nzp, d_ssr, d_flags, d_status, d_delta, d_V, d_A, d_rhs, d_aux, d_perm, d_ctb, d_tid, d_misc, d_gather,
+        d_nzp, d_ssr, d_flags, d_status, d_delta, d_V, d_A, d_rhs, d_aux, d_perm, d_ctb, d_cmask, d_tid, d_misc, d_gather,
         d_t0, d_t1, d_t2, d_t3, d_t4;  // small per-pass tables of the Gram path
     HostBuf h_stage, h_out;
     rr_stats stats{};
@@ -358,7 +358,7 @@ struct rr_engine {
         for (DevBuf *b : {&d_px, &d_pr, &d_pout}) b->release();
         for (DevBuf *b : {&X, &d_ins2, &d_chunks2, &d_cols2, &d_acc2, &d_ins, &d_chunks, &d_cols, &d_acc, &d_dots, &d_rdots, &d_tab, &d_rtab, &d_ws, &d_wsoff,
                           &d_list, &d_coef, &d_cs, &d_nzp, &d_ssr, &d_flags, &d_status, &d_delta, &d_V, &d_A, &d_rhs,
-                          &d_aux, &d_perm, &d_ctb, &d_tid, &d_misc, &d_gather, &d_t0, &d_t1, &d_t2, &d_t3, &d_t4})
+                          &d_aux, &d_perm, &d_ctb, &d_cmask, &d_tid, &d_misc, &d_gather, &d_t0, &d_t1, &d_t2, &d_t3, &d_t4})
             b->release();
         h_stage.release();
         h_out.release();
@@ -1395,6 +1395,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
         if (pc.err.empty() && !pc.wide.empty()) pc.err = pc.rb.bp->plan_gram(lim, cols, &pc.wide, false, pc.Pw, pc.tabw, pc.tabw_begin);
     };
     std::vector<int32_t> tab, tab_begin;
+    std::vector<uint32_t> cmask((size_t)nc, 0u);  // per candidate: terms that are constant by construction (rr_plan.h)
     {
         // the reduced dots of all pieces live in one vector: size it before the first launch
         size_t tab_total = 0;
@@ -1448,6 +1449,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
             e->stats.term_instances += pc.rb.bp->n_term_instances();
             e->stats.distinct_terms += pc.rb.bp->n_terms_distinct();
             e->stats.w_contract += pc.rb.bp->w_contract();
+            for (int32_t lc = 0; lc < pc.rb.c1 - pc.rb.c0; ++lc) cmask[(size_t)(pc.rb.c0 + lc)] = pc.rb.bp->cand_const_mask(lc);
         }
         if ((rc = reduce_over_ranks(e, &rr_engine::d_dots, 0, off, false))) { cudaStreamSynchronize(e->stream); return rc; }
         // per-candidate tables in candidate order
@@ -1488,8 +1490,10 @@ int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
     DevBuf &d_tabb = e->d_rtab;  // reused later for the residual tables; order of use is sequential
     if ((rc = upload(e, d_tabb, tab_begin.data(), tab_begin.size()))) return rc;
     if ((rc = upload(e, e->d_ctb, b->cand_term_begin, (size_t)nc + 1))) return rc;
+    if ((rc = upload(e, e->d_cmask, cmask.data(), cmask.size()))) return rc;
     rr::GramArgs g;
     g.dots = e->d_dots.as<double>();
+    g.cand_const = e->d_cmask.as<uint32_t>();
     g.cand_dot = e->d_tab.as<int32_t>();
     g.cand_dot_begin = d_tabb.as<int32_t>();
     g.list = nullptr;

@@ -276,6 +276,27 @@ std::string BatchPlanner::build_term(int32_t code_begin, int32_t code_len, Term 
     }
     if (st.size() != 1) return "postfix does not reduce to one tree";
     t.is_const_one = code_len == 1 && t.nodes[0].op == RR_OP_CONST && t.nodes[0].cval == 1.0;
+    {
+        // exact_const (rr_plan.h): bottom-up; two subtrees are identical when their postfix ranges are (constants by bits)
+        std::vector<char> kc(t.nodes.size(), 0);
+        auto same = [&](int32_t a, int32_t b) {
+            const int32_t la = a - t.nodes[a].first + 1, lb = b - t.nodes[b].first + 1;
+            if (la != lb) return false;
+            for (int32_t i = 0; i < la; ++i) {
+                const TermNode &x = t.nodes[t.nodes[a].first + i], &y = t.nodes[t.nodes[b].first + i];
+                if (x.op != y.op || x.var != y.var || std::memcmp(&x.cval, &y.cval, 8) != 0) return false;
+            }
+            return true;
+        };
+        for (size_t x = 0; x < t.nodes.size(); ++x) {
+            const TermNode &n = t.nodes[x];
+            if (n.op == RR_OP_CONST) kc[x] = 1;
+            else if (n.op == RR_OP_VAR) kc[x] = 0;
+            else if (n.right < 0) kc[x] = kc[n.left];
+            else kc[x] = (kc[n.left] && kc[n.right]) || ((n.op == RR_OP_DIVIDE || n.op == RR_OP_MINUS) && same(n.left, n.right));
+        }
+        t.exact_const = kc.back() != 0;
+    }
     return "";
 }
 

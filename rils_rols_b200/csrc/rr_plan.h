@@ -42,6 +42,11 @@ struct Term {
     std::vector<TermNode> nodes;           // postfix order, root = back()
     double w = 0.0;                        // SURVEY 8(d) contract weight of one evaluation
     bool is_const_one = false;
+    // the term has the same value at every sample BY CONSTRUCTION: no variable in it, or every variable sits under
+    // S / S or S - S of two identical subtrees (a local-search neighbourhood holds a few dozen of these: sin(c),
+    // t / t, ...). Its column is a multiple of the free term's; the solver is told, so that it drops one of the two
+    // like the reference's column-pivoted QR does instead of finding a singular Gram matrix and escalating.
+    bool exact_const = false;
 };
 
 struct SweepPlan {
@@ -90,6 +95,16 @@ public:
     const std::vector<int32_t> &term_ids() const { return term_id_; }  // per term instance -> distinct id
     const Term &term(int32_t u) const { return terms_[u]; }
     double w_contract() const { return w_contract_; }
+    // bit i set: term i of candidate c is exact_const (candidates with more than 32 terms report none)
+    uint32_t cand_const_mask(int32_t c) const
+    {
+        const int32_t t0 = b_->cand_term_begin[c], t1 = b_->cand_term_begin[c + 1];
+        if (t1 - t0 > 32) return 0u;
+        uint32_t m = 0;
+        for (int32_t t = t0; t < t1; ++t)
+            if (terms_[term_id_[t]].exact_const) m |= 1u << (t - t0);
+        return m;
+    }
     const std::vector<double> &cand_contract_w() const { return cand_w_; }
     // distinct terms (ascending ids) that contain shared sub-expression `sub`
     const std::vector<int32_t> &sub_occurrences(int32_t sub) const { return sub_occ_[sub]; }

@@ -80,16 +80,34 @@ __device__ inline void gather_gram(const double *dots, const int32_t *idx, int m
 // (ColPivHouseholderQR.h:517-527: the larger index loses the tie and ends below the threshold) and its
 // coefficient is 0. Deciding that from the ids instead of from rounding noise keeps such candidates out
 // of the double-double escalation. amap: alive column indices, the free term (index m) last.
-__device__ inline int alive_columns(const int32_t *idx, int m, int *amap)
+// The same for terms that are constant BY CONSTRUCTION (cmask, BatchPlanner::cand_const_mask: sin(c), t / t, ...):
+// their columns are exact multiples c_j of the free term's column of ones. Column-pivoted QR picks the longest of
+// these parallel columns when its turn comes (squared norms c_j^2 n against n, unchanged in proportion by the
+// reflectors before it; ties go to the lower index: ColPivHouseholderQR.h:517-522) and finds every other one at
+// exactly zero afterwards, below the threshold: coefficient 0. So: of the constant terms and the free term only the
+// one with the largest |c| stays (c_j = (t_j . 1) / n, which is exact for c = 1: t / t), ties to the lower index.
+__device__ inline int alive_columns(const int32_t *idx, int m, int *amap, uint32_t cmask, const double *G, int ldg, double n_total)
 {
+    int keep_const = m;  // the free term, c = 1
+    if (cmask && m <= 32) {
+        double best = 1.0;
+        for (int j = m - 1; j >= 0; --j)
+            if ((cmask >> j) & 1u) {
+                const double cj = fabs(G[j * ldg + m] / n_total);
+                if (cj >= best) { best = cj; keep_const = j; }  // descending j: on a tie the lower index wins
+            }
+    } else {
+        cmask = 0u;
+    }
     int na = 0;
     for (int j = 0; j < m; ++j) {
+        if (((cmask >> j) & 1u) && j != keep_const) continue;
         const int32_t dj = idx[j * m - j * (j - 1) / 2];  // id of t_j . t_j in the row-major upper triangle
         bool dup = false;
         for (int i = 0; i < j && !dup; ++i) dup = idx[i * m - i * (i - 1) / 2] == dj;
         if (!dup) amap[na++] = j;
     }
-    amap[na++] = m;
+    if (keep_const == m) amap[na++] = m;
     return na;
 }
 
@@ -188,6 +206,7 @@ struct GramArgs {
     const int32_t *cand_dot_begin;  // [n_list + 1]
     const int32_t *list;            // candidate ids (nullptr: identity)
     const int32_t *cand_term_begin; // batch offsets (k = terms + 1, coef offset = begin + c)
+    const uint32_t *cand_const;     // per candidate id: terms that are constant by construction (nullptr: none)
     int32_t n_list;
     double *ws;                     // workspace: per listed candidate 2*kk*kk + 10*kk doubles
     const int64_t *ws_begin;        // [n_list + 1] offsets into ws (doubles)
@@ -236,7 +255,7 @@ __global__ void rr_gram_solve(const GramArgs a)
     // workspace tail (4.5 kk doubles are free behind perm): alive map, compacted right-hand side and solution
     int *amap = perm + kk;
     double *rhs2 = reinterpret_cast<double *>(amap + kk), *x2 = rhs2 + kk;
-    const int na = alive_columns(idx, m, amap);
+    const int na = alive_columns(idx, m, amap, a.cand_const ? a.cand_const[c] : 0u, G, kk, a.k.n_total);
     for (int p = 0; p < na; ++p) {
         for (int q = 0; q < na; ++q) W[p * na + q] = G[amap[p] * kk + amap[q]];
         rhs2[p] = rhs[amap[p]];
@@ -259,8 +278,14 @@ __global__ void rr_gram_solve(const GramArgs a)
     const double ynorm2 = a.k.sst + a.k.n_total * a.k.y_mean * a.k.y_mean;
     (void)cmax;
     bool ambiguous = false;
+    uint64_t alive_bits = 0;  // (kk <= 64 wherever a column is dropped structurally; wider candidates have all alive)
+    for (int p = 0; p < na; ++p)
+        if (amap[p] < 64) alive_bits |= 1ull << amap[p];
     for (int i = 0; i < kk; ++i) {
         cs[i] = snap_coef(coef[i], i == m);
+        // a column dropped by construction (a duplicate, a constant term) has the coefficient 0 exactly, as in the
+        // reference: nothing to decide
+        if (na < kk && i < 64 && !((alive_bits >> i) & 1ull)) continue;
         const double gii = G[i * kk + i];
         const double cerr = 64.0 * (DBL_EPSILON / fmax(rho_min, DBL_MIN)) * sqrt(ynorm2 / fmax(gii, DBL_MIN));
         const double d0 = fabs(fabs(coef[i]) - RR_EPS_SNAP);
@@ -311,7 +336,7 @@ __global__ void rr_refine_update(const RefineArgs a)
     gather_gram(a.g.dots, idx, m, a.g.k, G, kk, b);
     int *amap = perm + kk;
     double *g2 = reinterpret_cast<double *>(amap + kk), *x2 = g2 + kk;
-    const int na = alive_columns(idx, m, amap);  // see rr_gram_solve
+    const int na = alive_columns(idx, m, amap, a.g.cand_const ? a.g.cand_const[c] : 0u, G, kk, a.g.k.n_total);  // see rr_gram_solve
     for (int p = 0; p < na; ++p)
         for (int q = 0; q < na; ++q) W[p * na + q] = G[amap[p] * kk + amap[q]];
     double rho_min;
