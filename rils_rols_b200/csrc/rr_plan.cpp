@@ -293,7 +293,17 @@ std::string BatchPlanner::build_term(int32_t code_begin, int32_t code_len, Term 
             if (n.op == RR_OP_CONST) kc[x] = 1;
             else if (n.op == RR_OP_VAR) kc[x] = 0;
             else if (n.right < 0) kc[x] = kc[n.left];
-            else kc[x] = (kc[n.left] && kc[n.right]) || ((n.op == RR_OP_DIVIDE || n.op == RR_OP_MINUS) && same(n.left, n.right));
+            else {
+                // (c * S) / S, S / (c * S), (c * S) / (c' * S): constant up to the rounding of the products
+                auto core = [&](int32_t y) -> int32_t {
+                    const TermNode &q = t.nodes[y];
+                    if (q.op == RR_OP_MULTIPLY && t.nodes[q.left].op == RR_OP_CONST) return q.right;
+                    if ((q.op == RR_OP_MULTIPLY || q.op == RR_OP_DIVIDE) && t.nodes[q.right].op == RR_OP_CONST) return q.left;
+                    return y;
+                };
+                kc[x] = (kc[n.left] && kc[n.right]) || ((n.op == RR_OP_DIVIDE || n.op == RR_OP_MINUS) && same(n.left, n.right)) ||
+                        (n.op == RR_OP_DIVIDE && same(core(n.left), core(n.right)));
+            }
         }
         t.exact_const = kc.back() != 0;
     }

@@ -43,9 +43,11 @@ struct Term {
     double w = 0.0;                        // SURVEY 8(d) contract weight of one evaluation
     bool is_const_one = false;
     // the term has the same value at every sample BY CONSTRUCTION: no variable in it, or every variable sits under
-    // S / S or S - S of two identical subtrees (a local-search neighbourhood holds a few dozen of these: sin(c),
-    // t / t, ...). Its column is a multiple of the free term's; the solver is told, so that it drops one of the two
-    // like the reference's column-pivoted QR does instead of finding a singular Gram matrix and escalating.
+    // S / S, S - S or (c S) / S of identical subtrees (a local-search neighbourhood holds a few dozen of these: sin(c),
+    // t / t, (c t) / t, ...; the last kind is constant up to the rounding of its products). Its column is a multiple
+    // of the free term's; the solver is told, so that it keeps one of the two by the reference's pivot rule (what
+    // column-pivoted QR does in exact arithmetic, and what the double-double escalation arrives at a sweep later)
+    // instead of finding a singular Gram matrix and escalating.
     bool exact_const = false;
 };
 

@@ -81,7 +81,9 @@ __device__ inline void gather_gram(const double *dots, const int32_t *idx, int m
 // coefficient is 0. Deciding that from the ids instead of from rounding noise keeps such candidates out
 // of the double-double escalation. amap: alive column indices, the free term (index m) last.
 // The same for terms that are constant BY CONSTRUCTION (cmask, BatchPlanner::cand_const_mask: sin(c), t / t, ...):
-// their columns are exact multiples c_j of the free term's column of ones. Column-pivoted QR picks the longest of
+// their columns are multiples c_j of the free term's column of ones (exact, or up to the rounding of (c t) / t). In
+// exact arithmetic - the reference's floating-point QR sometimes keeps both with coefficients of +-1e15 instead, by
+// rounding residue: SURVEY App. B.6 - column-pivoted QR picks the longest of
 // these parallel columns when its turn comes (squared norms c_j^2 n against n, unchanged in proportion by the
 // reflectors before it; ties go to the lower index: ColPivHouseholderQR.h:517-522) and finds every other one at
 // exactly zero afterwards, below the threshold: coefficient 0. So: of the constant terms and the free term only the

@@ -59,9 +59,11 @@ def term_columns(Xfm, batch: B.Batch, c: int, evaluate):
     """The candidate's design matrix as the reference builds it (rils_rols_cpp.cpp:477-482): one column per
     factor, ones last. Columns of repeated terms are evaluated once per data set (a local-search
     neighbourhood repeats 90 % of its terms)."""
-    if _COL_CACHE_ID[0] != id(Xfm):
+    # (id() alone is not an identity: a freed array's id is reused by the next test's data set)
+    ident = (id(Xfm), Xfm.shape, float(Xfm[0, 0]), float(Xfm[-1, -1]), float(Xfm[0, Xfm.shape[1] // 2]))
+    if _COL_CACHE_ID[0] != ident:
         _COL_CACHE.clear()
-        _COL_CACHE_ID[0] = id(Xfm)
+        _COL_CACHE_ID[0] = ident
     t0, t1 = int(batch.cand_term_begin[c]), int(batch.cand_term_begin[c + 1])
     cols = []
     for t in range(t0, t1):

@@ -617,3 +617,49 @@ def test_row_machine_matches_the_accumulator_machine_and_the_oracle(golden, monk
     assert rep["well_posed"] >= 80, rep
     print(f"\nR8 vs G8 at n = {n}: max relative SSR difference {err.max():.2e} over {int(plain.sum())} candidates; "
           f"{st_r['row_groups']} groups, {st_r['row_group_rows'] / st_r['row_groups']:.2f} rows per group; vs oracle: {rep}")
+
+
+def test_constant_terms_follow_the_reference_pivot_rule_without_escalation():
+    """A term that is constant by construction (sin(c), t / t, t - t) is a multiple of the free term's column. In exact
+    arithmetic the reference's column-pivoted QR keeps the longer of the two parallel columns (ties: the lower index)
+    and gives the other the coefficient 0 (ColPivHouseholderQR.h:517-527, 606); in floating point it does so or keeps
+    both with coefficients of +-1e15 depending on rounding residue. On the Gram path the solver is
+    told which terms are such constants and applies the exact-arithmetic rule instead of finding a singular Gram
+    matrix and escalating to double-double (which arrives at the same answer a sweep later). Expected values: the
+    reference's fit of the design WITHOUT the constant term."""
+    v = B.Expr.var
+    n = 20000
+    rng = np.random.default_rng(7)
+    X = rng.uniform(0.2, 3.0, size=(n, 4))
+    y = 1.5 * X[:, 0] - 0.7 * X[:, 1] * X[:, 2] + 2.0 + 0.05 * rng.standard_normal(n)
+    consts = [  # (term, its value, does the term stay?)
+        (B.sin(B.Expr.const(2.017)), np.sin(2.017), False),  # 0.90: shorter than ones
+        (B.exp(B.Expr.const(2.017)), np.exp(2.017), True),   # 7.5: longer than ones, the free term is dropped
+        (v(3) / v(3), 1.0, True),                            # a tie: the lower index (the term) stays
+        (v(3) - v(3), 0.0, False),
+        (B.sqr(B.Expr.const(2.017)) / B.sqrt(v(3) / v(3)), 2.017 * 2.017, True),
+        (B.ln(B.Expr.const(2.017)), np.log(2.017), False),
+        ((2.5 * v(3)) / v(3), 2.5, True),                    # constant up to the rounding of the product
+        (v(3) / (4.0 * v(3)), 0.25, False),
+        ((0.5 * B.sin(v(3))) / (B.sin(v(3)) * 2.0), 0.25, False),
+    ]
+    cands = [[v(0), v(1) * v(2), k] for k, _, _ in consts]
+    batch = B.Batch.from_exprs(B.MODE_OLS_FIT, cands)
+    Xfm = O.feature_major(X)
+    reduced = B.Batch.from_exprs(B.MODE_OLS_FIT, [[v(0), v(1) * v(2)]])
+    ored, f0, _, _ = O.score_batch(Xfm, y, reduced)
+    a, b, icpt = ored.coef[:3]
+    ssr_ref = f0[0] * float(((y - y.mean()) ** 2).sum())
+    with Engine(X, y) as eng:
+        assert eng.info().exact_max_n < n
+        res = eng.score(batch)
+        st = eng.stats()
+    assert st["dd"] == 0 and st["exact"] == 0, st
+    for c, (_, val, stays) in enumerate(consts):
+        cg = res.coef[batch.coef_slice(c)]
+        want = np.array([a, b, icpt / val, 0.0]) if stays else np.array([a, b, 0.0, icpt])
+        assert res.flags[c] & B.RES_RANKDEF and not res.flags[c] & B.RES_DD, (c, hex(int(res.flags[c])))
+        assert res.nonzero_pivots[c] == 3, (c, res.nonzero_pivots[c])
+        assert np.array_equal(cg == 0.0, want == 0.0), (c, cg, want)
+        assert np.allclose(cg, want, rtol=1e-9, atol=1e-9 * np.max(np.abs(want))), (c, cg, want)
+        assert abs(res.ssr[c] - ssr_ref) <= 1e-9 * ssr_ref, (c, res.ssr[c], ssr_ref)
