@@ -278,7 +278,7 @@ std::string BatchPlanner::build_term(int32_t code_begin, int32_t code_len, Term 
     t.is_const_one = code_len == 1 && t.nodes[0].op == RR_OP_CONST && t.nodes[0].cval == 1.0;
     {
         // exact_const (rr_plan.h): bottom-up; two subtrees are identical when their postfix ranges are (constants by bits)
-        std::vector<char> kc(t.nodes.size(), 0);
+        std::vector<char> kc(t.nodes.size(), 0), kz(t.nodes.size(), 0);  // constant / zero at every sample
         auto same = [&](int32_t a, int32_t b) {
             const int32_t la = a - t.nodes[a].first + 1, lb = b - t.nodes[b].first + 1;
             if (la != lb) return false;
@@ -290,10 +290,19 @@ std::string BatchPlanner::build_term(int32_t code_begin, int32_t code_len, Term 
         };
         for (size_t x = 0; x < t.nodes.size(); ++x) {
             const TermNode &n = t.nodes[x];
-            if (n.op == RR_OP_CONST) kc[x] = 1;
-            else if (n.op == RR_OP_VAR) kc[x] = 0;
-            else if (n.right < 0) kc[x] = kc[n.left];
-            else {
+            if (n.op == RR_OP_CONST) {
+                kc[x] = 1;
+                kz[x] = n.cval == 0.0;
+            } else if (n.op == RR_OP_VAR) {
+                kc[x] = 0;
+            } else if (n.right < 0) {
+                kc[x] = kc[n.left];
+                kz[x] = kz[n.left] && (n.op == RR_OP_SQRT || n.op == RR_OP_SQR || n.op == RR_OP_SIN);
+            } else {
+                // zero columns: S - S, 0 * S, 0 / S (where the other side is not finite the result is NaN at that
+                // sample, the reductions see it and the candidate gets the sentinel before anything is dropped)
+                kz[x] = (n.op == RR_OP_MINUS && same(n.left, n.right)) || (n.op == RR_OP_MULTIPLY && (kz[n.left] || kz[n.right])) ||
+                        (n.op == RR_OP_DIVIDE && kz[n.left]);
                 // (c * S) / S, S / (c * S), (c * S) / (c' * S): constant up to the rounding of the products
                 auto core = [&](int32_t y) -> int32_t {
                     const TermNode &q = t.nodes[y];
@@ -301,7 +310,7 @@ std::string BatchPlanner::build_term(int32_t code_begin, int32_t code_len, Term 
                     if ((q.op == RR_OP_MULTIPLY || q.op == RR_OP_DIVIDE) && t.nodes[q.right].op == RR_OP_CONST) return q.left;
                     return y;
                 };
-                kc[x] = (kc[n.left] && kc[n.right]) || ((n.op == RR_OP_DIVIDE || n.op == RR_OP_MINUS) && same(n.left, n.right)) ||
+                kc[x] = kz[x] || (kc[n.left] && kc[n.right]) || ((n.op == RR_OP_DIVIDE || n.op == RR_OP_MINUS) && same(n.left, n.right)) ||
                         (n.op == RR_OP_DIVIDE && same(core(n.left), core(n.right)));
             }
         }

@@ -642,6 +642,8 @@ def test_constant_terms_follow_the_reference_pivot_rule_without_escalation():
         ((2.5 * v(3)) / v(3), 2.5, True),                    # constant up to the rounding of the product
         (v(3) / (4.0 * v(3)), 0.25, False),
         ((0.5 * B.sin(v(3))) / (B.sin(v(3)) * 2.0), 0.25, False),
+        ((B.sqrt(v(3)) - B.sqrt(v(3))) / v(1), 0.0, False),   # zero columns
+        (B.sqrt(v(3) - v(3)) * v(0), 0.0, False),
     ]
     cands = [[v(0), v(1) * v(2), k] for k, _, _ in consts]
     batch = B.Batch.from_exprs(B.MODE_OLS_FIT, cands)

@@ -33,7 +33,7 @@ b = W.cfg5_neighbourhood()
 with Engine(X, y) as eng:
     r = eng.score(b)
 fl = np.asarray(r.flags)
-for name, bit in (("dd", B.RES_DD), ("rankdef", B.RES_RANKDEF)):
+for name, bit in (("dd", B.RES_DD), ("refined", B.RES_REFINED), ("rankdef", B.RES_RANKDEF)):
     idx = np.nonzero(fl & bit)[0]
     print(f"== {name}: {len(idx)} candidates")
     for c in idx[:60]:
