@@ -1365,6 +1365,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
     rr::PlanLimits lim_g8 = lim;
     lim_g8.tile_cols = g8_tile_cols();
     lim_g8.g8 = true;
+    lim_g8.ins_window = rr::kG8Window;
     lim_g8.mdot_rows = false;
     // R8 plans (the row machine, rr_sweep_r8.cuh) on request (RR_B200_R8=1): measured slower than G8 plans on the headline
     // neighbourhood ("the row machine"), so they are not the default. A piece whose rows do not fill their

@@ -42,6 +42,7 @@ static_assert(sizeof(RRIns) == 16, "RRIns must be 16 bytes");
 // from the chunk's first instruction. USEP and its consumer must sit in the same window (the redirected
 // operand lives in registers that do not survive a window switch): the planner pads with RI_NOP.
 #define RR_INS_WINDOW 64
+#define RR_G8_INS_WINDOW 32  // G8 plans (rr_sweep_g8.cuh)
 
 enum RRInsOp : uint32_t {
     RI_END = 0,

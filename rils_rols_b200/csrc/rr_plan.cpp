@@ -1259,7 +1259,7 @@ struct BatchPlanner::Chunk {
                 const uint32_t op = RR_OP(P.ins[i].w0);
                 const bool pair_head = (op >= RI_USEP0 && op < RI_USEP0 + RR_NREG) || (lim.mdot_rows && !g8 && carries_mdot(P.ins[i])) ||
                                        op == RI_GRAM8;
-                if (pair_head && out.size() % RR_INS_WINDOW == RR_INS_WINDOW - 1)
+                if (pair_head && out.size() % (size_t)lim.ins_window == (size_t)lim.ins_window - 1)
                     out.push_back(nop);
                 out.push_back(P.ins[i]);
             }
@@ -2781,6 +2781,7 @@ extern "C" int rr_debug_plan_batch(const rr_batch *batch, int32_t d, int32_t kin
         }
         case 6:
             lim.g8 = true;
+            lim.ins_window = RR_G8_INS_WINDOW;
             err = bp.plan_gram_g8(lim, cols, nullptr, P, tab, tab_begin);
             break;
         case 7: err = bp.plan_gram_r8(lim, cols, nullptr, P, tab, tab_begin); break;

@@ -77,6 +77,7 @@ struct PlanLimits {
     bool no_cse = false;
     bool fuse = true;  // super-instruction peephole (rr_isa.h)
     bool g8 = false;         // G8 plan (rr_isa.h RI_GRAM8): fresh terms in tile slots, reductions by DMMA against the pins
+    int32_t ins_window = RR_INS_WINDOW;  // instructions per shared-memory window of the kernel that runs the plan
     bool mdot_rows = false;  // data slot with the ring rows behind every instruction that ends in RI_MDOT (rr_isa.h)
 };
 

@@ -21,7 +21,11 @@ constexpr int kG8Tile = 512;                       // samples per tile
 constexpr uint32_t kG8ColBytes = kG8Tile * 8 + 32;  // padded column stride
 constexpr uint32_t kG8HalfBytes = kG8Tile * 4;
 constexpr uint32_t kG8StageBytes = 4 * 80 * 8;      // 4 warps x 80 outputs
-constexpr size_t kG8StaticBytes = 2 * (kInsWindow + 2) * 16 + 4 * 8;
+// instruction windows of 32 (the other kernels stream 64 at a time): the kilobyte that frees, with what was spare, is
+// the tile's 27th column - a seventh row slot next to 20 staged features, and a group of seven rows costs the DMMA
+// pipe what a group of six does
+constexpr int kG8Window = RR_G8_INS_WINDOW;
+constexpr size_t kG8StaticBytes = 2 * (kG8Window + 2) * 16 + 4 * 8;
 static_assert(kG8ColBytes == 4128 && kG8HalfBytes == 2048, "rr_sweep_core_g8.cuh is written for this geometry");
 constexpr size_t g8_dyn_smem(int cols) { return (size_t)kG8StageBytes + (size_t)cols * kG8ColBytes; }
 
@@ -30,15 +34,15 @@ __global__ void __launch_bounds__(kG8Threads, 2) rr_sweep_g8_kernel(const SweepA
     constexpr int T = kG8Tile;
     extern __shared__ __align__(128) unsigned char rr_dyn[];  // [staging][tile]
     __shared__ __align__(16) unsigned char rr_static[kG8StaticBytes];
-    uint4(*ibuf)[kInsWindow + 2] = reinterpret_cast<uint4(*)[kInsWindow + 2]>(rr_static);
-    uint64_t &mbar_tile = *reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16);
-    uint64_t *mbar_ins = reinterpret_cast<uint64_t *>(rr_static + 2 * (kInsWindow + 2) * 16 + 16);
+    uint4(*ibuf)[kG8Window + 2] = reinterpret_cast<uint4(*)[kG8Window + 2]>(rr_static);
+    uint64_t &mbar_tile = *reinterpret_cast<uint64_t *>(rr_static + 2 * (kG8Window + 2) * 16);
+    uint64_t *mbar_ins = reinterpret_cast<uint64_t *>(rr_static + 2 * (kG8Window + 2) * 16 + 16);
 
     const RRChunk ch = a.chunks[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t g = (uint32_t)lane >> 2, q = (uint32_t)lane & 3u;
     const uint4 *prog = reinterpret_cast<const uint4 *>(a.ins + ch.pc_begin);
-    const int n_win = (ch.n_ins + kInsWindow - 1) / kInsWindow;
+    const int n_win = (ch.n_ins + kG8Window - 1) / kG8Window;
     const uint32_t tbase = (uint32_t)tid * 16u;  // this thread's sample pair inside a column half
     const uint32_t dyn_sh = smem_u32(rr_dyn);
     const uint32_t stage_sh = dyn_sh;
@@ -60,10 +64,10 @@ __global__ void __launch_bounds__(kG8Threads, 2) rr_sweep_g8_kernel(const SweepA
         mbar_init(&mbar_ins[0], 1);
         mbar_init(&mbar_ins[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        ibuf[0][kInsWindow] = make_uint4(RI_WINEND, 0, 0, 0);
-        ibuf[1][kInsWindow] = make_uint4(RI_WINEND, 0, 0, 0);
-        ibuf[0][kInsWindow + 1] = make_uint4(RI_END, 0, 0, 0);
-        ibuf[1][kInsWindow + 1] = make_uint4(RI_END, 0, 0, 0);
+        ibuf[0][kG8Window] = make_uint4(RI_WINEND, 0, 0, 0);
+        ibuf[1][kG8Window] = make_uint4(RI_WINEND, 0, 0, 0);
+        ibuf[0][kG8Window + 1] = make_uint4(RI_END, 0, 0, 0);
+        ibuf[1][kG8Window + 1] = make_uint4(RI_END, 0, 0, 0);
     }
     __syncthreads();
     uint32_t tile_parity = 0, ins_parity0 = 0, ins_parity1 = 0;
@@ -81,8 +85,8 @@ __global__ void __launch_bounds__(kG8Threads, 2) rr_sweep_g8_kernel(const SweepA
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (lane == 0) {
                 mbar_expect_tx(&mbar_tile, (uint32_t)(ch.n_cols * T * 8));
-                mbar_expect_tx(&mbar_ins[0], (uint32_t)(kInsWindow * 16));
-                tma_load_1d(&ibuf[0][0], prog, (uint32_t)(kInsWindow * 16), &mbar_ins[0]);
+                mbar_expect_tx(&mbar_ins[0], (uint32_t)(kG8Window * 16));
+                tma_load_1d(&ibuf[0][0], prog, (uint32_t)(kG8Window * 16), &mbar_ins[0]);
             }
             __syncwarp();
             for (int c = lane; c < ch.n_cols; c += 32)
@@ -109,8 +113,8 @@ __global__ void __launch_bounds__(kG8Threads, 2) rr_sweep_g8_kernel(const SweepA
             __syncthreads();  // every warp has finished window win-1, so its buffer (the other one) may be refilled
             if (tid == 0 && win + 1 < n_win) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&mbar_ins[b ^ 1], (uint32_t)(kInsWindow * 16));
-                tma_load_1d(&ibuf[b ^ 1][0], prog + (size_t)(win + 1) * kInsWindow, (uint32_t)(kInsWindow * 16), &mbar_ins[b ^ 1]);
+                mbar_expect_tx(&mbar_ins[b ^ 1], (uint32_t)(kG8Window * 16));
+                tma_load_1d(&ibuf[b ^ 1][0], prog + (size_t)(win + 1) * kG8Window, (uint32_t)(kG8Window * 16), &mbar_ins[b ^ 1]);
             }
             if (b == 0) { mbar_wait(&mbar_ins[0], ins_parity0); ins_parity0 ^= 1u; }
             else { mbar_wait(&mbar_ins[1], ins_parity1); ins_parity1 ^= 1u; }
