@@ -290,6 +290,10 @@ RR_API void rr_debug_plan_free(rr_debug_plan *p);
  * one after the other (rr_score_batch plans the second half of a large neighbourhood on a helper thread).
  * 0 = identical, 1 = different, RR_ERR_INVALID = malformed batch. */
 RR_API int rr_debug_plan_concurrency_check(const rr_batch *batch, int32_t d, int32_t tile_cols);
+/* Host-only test hook: per candidate, bit i set = term i is constant by construction (no variable in it, t / t,
+ * t - t, (c t) / t, 0 * t, ...). The Gram-path solver keeps such a column or the free term - the longer of the two,
+ * the reference's pivot rule - instead of escalating a singular Gram matrix. out: n_cand words. */
+RR_API int rr_debug_const_terms(const rr_batch *batch, int32_t d, uint32_t *out);
 
 /* Last error text: of the engine, or of the calling thread when e == NULL. */
 RR_API const char *rr_last_error(const rr_engine *e);

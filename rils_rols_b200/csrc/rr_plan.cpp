@@ -2849,6 +2849,19 @@ extern "C" int rr_debug_plan_concurrency_check(const rr_batch *batch, int32_t d,
     return 0;
 }
 
+extern "C" int rr_debug_const_terms(const rr_batch *batch, int32_t d, uint32_t *out)
+{
+    if (!batch || !out) return RR_ERR_INVALID;
+    try {
+        rr::BatchPlanner bp(batch, d);
+        if (!bp.analyse(false).empty()) return RR_ERR_INVALID;
+        for (int32_t c = 0; c < batch->n_cand; ++c) out[c] = bp.cand_const_mask(c);
+    } catch (...) {
+        return RR_ERR_NOMEM;
+    }
+    return RR_OK;
+}
+
 extern "C" void rr_debug_plan_free(rr_debug_plan *p)
 {
     if (!p) return;

@@ -22,7 +22,7 @@ EXPORTS = [
     "rr_engine_destroy", "rr_comm_unique_id", "rr_engine_comm_init", "rr_engine_set_allreduce", "rr_engine_get_info",
     "rr_get_stats", "rr_score_batch", "rr_classifier_metrics", "rr_predict", "rr_predict_rowmajor",
     "rr_predict_proba_rowmajor", "rr_feature_r2", "rr_engine_read_rows", "rr_measure_fp64_peak",
-    "rr_debug_plan_batch", "rr_debug_plan_free", "rr_debug_plan_concurrency_check",
+    "rr_debug_plan_batch", "rr_debug_plan_free", "rr_debug_plan_concurrency_check", "rr_debug_const_terms",
 ]
 ABI_VERSION = 3
 

@@ -496,3 +496,31 @@ def test_g8_plan_rejects_wide_candidates():
     wide = B.Batch.from_exprs(B.MODE_OLS_FIT, [[v(i % 3) * float(i + 2) + B.sin(v(i % 3) * float(i)) for i in range(9)]])
     with pytest.raises(ValueError, match="too wide"):
         EMU.Plan(wide, 3, EMU.KIND_GRAM_G8, tile_cols=26)
+
+
+def test_terms_constant_by_construction_are_recognised():
+    """The planner marks terms whose column is a multiple of the free term's by construction (rr_plan.h Term::exact_const);
+    the Gram-path solver uses the marks to keep one of the two parallel columns by the reference's pivot rule instead of
+    escalating a singular Gram matrix (GPU: test_constant_terms_follow_the_reference_pivot_rule_without_escalation)."""
+    import ctypes as C
+
+    v, k = B.Expr.var, B.Expr.const
+    S = B.sin(k(1.0) / v(0))
+    cases = [
+        (B.sin(k(2.017)), True), (k(3.0) * B.exp(k(0.5)), True),            # no variable
+        (S / S, True), (v(1) / v(1), True), (S - S, True),                    # t / t, t - t
+        ((k(0.5) * S) / S, True), (S / (S * k(2.0)), True), ((k(0.5) * S) / (k(3.0) * S), True),
+        (B.sqrt(v(2) - v(2)) / v(1), True), ((S - S) * v(1), True), (k(0.0) * v(1), True),  # zero columns
+        (B.cos(v(2) - v(2)), True),                                            # cos(0) = 1
+        (S / B.sin(k(1.0) / v(1)), False), (S * S, False), (v(0) / (v(0) + k(1.0)), False), (S + S, False),
+        (B.cos(k(6.2e-05) * S), False), ((S / v(1)) * v(1), False),
+    ]
+    batch = B.Batch.from_exprs(B.MODE_OLS_FIT, [[v(0), e, v(1) * v(2)] for e, _ in cases])
+    L = E.lib()
+    L.rr_debug_const_terms.argtypes = [C.POINTER(B.rr_batch), C.c_int32, C.POINTER(C.c_uint32)]
+    L.rr_debug_const_terms.restype = C.c_int
+    out = (C.c_uint32 * batch.n_cand)()
+    bs = batch.as_struct()
+    assert L.rr_debug_const_terms(C.byref(bs), 3, out) == 0
+    for c, (_, want) in enumerate(cases):
+        assert out[c] == (2 if want else 0), (c, out[c], want)
