@@ -38,10 +38,11 @@ UNIT = "tree-samples/s"
 
 def load_traffic():
     """dram bytes per launch of the dominant kernel, from the committed ncu --set full capture"""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            return json.load(f).get("traffic")
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                return json.load(f).get("traffic")
     return None
 
 
@@ -422,7 +423,7 @@ def main():
             "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
             "clocks": clocks,
             "roofline": {
-                "bound": "fp64", "kernel": "rr_sweep_kernel", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12,
+                "bound": "fp64", "kernel": "rr_sweep_g8_kernel", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12,
                 "unit": "T fp64-pipe thread-instr/s", "frac": achieved / fp64_peak,
                 "peak_source": "measured live: DFMA-only microkernel on this GPU (rr_measure_fp64_peak)",
                 "traffic": load_traffic() if int(info.n) == (1 << 24) else None,
