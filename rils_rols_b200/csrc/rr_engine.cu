@@ -1359,7 +1359,7 @@ int run_gram(rr_engine *e, const rr_batch *b, rr_result *res)
             Piece &pc = pieces[i];
             pc.rb.init(b, cut[i], cut[i + 1], e->d);
             pc.g8 = use_g8;
-            for (int32_t c = cut[i]; c < cut[i + 1]; ++c) (use_g8 && k_of(c) - 1 > RR_NPIN ? pc.wide : pc.narrow).push_back(c - cut[i]);
+            for (int32_t c = cut[i]; c < cut[i + 1]; ++c) (use_g8 && k_of(c) - 1 > RR_NPIN - 1 ? pc.wide : pc.narrow).push_back(c - cut[i]);
         }
     }
     rr::PlanLimits lim_g8 = lim;

@@ -72,7 +72,8 @@ enum RRInsOp : uint32_t {
     // pins with DMMA.8x8x4 (a warp-level 8 terms x 8 pins x 4 samples product-accumulate per instruction: the
     // accumulator fragment IS the warp total, nothing is transposed) plus each row's t.t and sum(t).
     // w0 = RI_GRAM8 | n_rows << 8; w1, lo32(imm), hi32(imm) = 80 "wanted" bits, bit 10 g + o of row g: o = 0..7 pin o,
-    // 8 = t.t, 9 = sum(t); output ids are consecutive from the chunk's running count in bit order. A data slot
+    // 8 = t.t, 9 = unused (a row's sum(t) is its product with pin 7, which G8 plans hold at a column of ones: the
+    // kernel forms no sum of its own and the planner never sets the bit); output ids are consecutive from the chunk's running count in bit order. A data slot
     // (RI_NOP, aux RR_GRAM_COLS) follows: bytes 4..11 = the tile column of each row (unused rows repeat row 0).
     RI_GRAM8,
     // pin j (aux = j) <- engine column w1 read from global memory, as a reduction partner only (B fragment)

@@ -525,6 +525,18 @@ struct BatchPlanner::Chunk {
         pin_term[0] = PIN_RESERVED;
         return PINREF | 0u;
     }
+    // G8 plans: the last pin <- a column of ones, held until the chunk ends. A row's sum(t) is then one more of the
+    // products RI_GRAM8 forms anyway (t . pin), and the kernel keeps no running sum of its own.
+    void reserve_pin_ones()
+    {
+        emit(RI_LOAD_C, 0, 1.0, 0);
+        const int32_t sl = alloc_slot(-2);
+        if (!err.empty()) return;
+        emit(RI_ST, (uint32_t)sl, 0.0, 0);
+        emit(RI_PINB0 + (uint32_t)(RR_NPIN - 1), (uint32_t)sl, 0.0, 0);
+        free_slot(sl);
+        pin_term[RR_NPIN - 1] = PIN_RESERVED;
+    }
     int32_t free_pins() const
     {
         int32_t f = 0;
@@ -1541,7 +1553,8 @@ std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols
         for (int32_t t = b_->cand_term_begin[c]; t < b_->cand_term_begin[c + 1]; ++t)
             units[i].terms.push_back(term_id_[t]);
         units[i].w = cand_w_[c];
-        if ((int32_t)units[i].terms.size() > RR_NPIN) return "candidate too wide for a G8 plan";
+        // a row meets its partners as pins: the other terms, the centred target and the column of ones
+        if ((int32_t)units[i].terms.size() > RR_NPIN - 1) return "candidate too wide for a G8 plan";
     }
     std::vector<std::vector<int32_t>> term_units(terms_.size());
     for (size_t i = 0; i < units.size(); ++i)
@@ -1564,10 +1577,13 @@ std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols
     };
     std::vector<int32_t> ids;
     int32_t prev_m = 0, prev_T[RR_NPIN], prev_pid[RR_NPIN][RR_NPIN + 2];
+    (void)prev_T;
     for (const ChunkSpec &cs : specs) {
         Chunk ch(*this, P, lim, cs.cols, RR_NPIN);
         ch.g8 = true;
         ch.reserve_pin_global(cols.yc);  // pin 0, for the whole chunk
+        ch.reserve_pin_ones();           // pin 7: sum(t) of every row comes out of the DMMA like its other products
+        if (!ch.err.empty()) return ch.err;
         for (int32_t ui = cs.begin; ui < cs.end; ++ui) {
             const std::vector<int32_t> &T = units[ui].terms;
             const int32_t m = (int32_t)T.size();
@@ -1643,7 +1659,15 @@ std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols
                 uint32_t pin_mask = with_yc ? 1u : 0u;
                 uint64_t pin_key[RR_NPIN];
                 int64_t pin_partner_term[RR_NPIN];
-                if (with_yc) pin_key[0] = key(u, KEY_YC);
+                if (with_yc) {
+                    pin_key[0] = key(u, KEY_YC);
+                    pin_partner_term[0] = KEY_YC;
+                }
+                if (one) {
+                    pin_mask |= 1u << (RR_NPIN - 1);
+                    pin_key[RR_NPIN - 1] = key(u, KEY_ONE);
+                    pin_partner_term[RR_NPIN - 1] = KEY_ONE;
+                }
                 for (int32_t v : done) {
                     if (v == u || !missing(u, v)) continue;
                     const int j = ch.pin_partner(v);
@@ -1660,23 +1684,18 @@ std::string BatchPlanner::plan_gram_g8(const PlanLimits &lim, const ColIds &cols
                     transient = it == occ.end() || *it > ui + lim.transient_horizon;
                 }
                 ids.clear();
-                ch.add_row(u, pin_mask, self, one, !transient, ids);
+                ch.add_row(u, pin_mask, self, false, !transient, ids);
                 if (!ch.err.empty()) return ch.err;
                 size_t k = 0;
                 for (int j = 0; j < RR_NPIN; ++j)
                     if ((pin_mask >> j) & 1u) {
                         dots.set(pin_key[j], ids[k]);
-                        if (j > 0) slot(u, pin_partner_term[j]) = ids[k];
-                        else pid[index_of(u)][m] = ids[k];
+                        slot(u, pin_partner_term[j]) = ids[k];
                         ++k;
                     }
                 if (self) {
                     dots.set(key(u, u), ids[k]);
                     slot(u, u) = ids[k++];
-                }
-                if (one) {
-                    dots.set(key(u, KEY_ONE), ids[k]);
-                    pid[index_of(u)][m + 1] = ids[k++];
                 }
                 done.push_back(u);
             }

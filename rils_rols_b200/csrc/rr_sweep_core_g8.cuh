@@ -128,17 +128,18 @@ static_assert(RI_OPCOUNT == 159, "update the jump table of rr_core_g8");
 #define RR_G8_OFFV_13 "416"
 #define RR_G8_OFFV_14 "448"
 #define RR_G8_OFFV_15 "480"
-// one step of the group: A element from the row's slot, DMMA against the B fragment, the row's own t.t and sum(t)
-// (D0, D1) / S2 / S1: the accumulators of this step's chain - even and odd steps run two independent chains, a
+// one step of the group: A element from the row's slot, DMMA against the B fragment, the row's own t.t (sum(t) is the
+// product with the last pin, which G8 plans keep at a column of ones: BatchPlanner::Chunk::reserve_pin_ones)
+// (D0, D1) / S2: the accumulators of this step's chain (S1 is unused) - even and odd steps run two independent chains, a
 // dependent DMMA every 32 cycles per warp would leave the pipe half idle
 #define RR_G8_STEP_LO(s, A, D0, D1, S2, S1)                                                              \
     "ld.shared.f64 " A ", [wp+" RR_G8_OFF_LO(s) "];\n"                                                   \
     "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {" D0 ", " D1 "}, {" A "}, {" RR_PB(s) "}, {" D0 ", " D1 "};\n" \
-    "fma.rn.f64 " S2 ", " A ", " A ", " S2 ";\n add.rn.f64 " S1 ", " S1 ", " A ";\n"
+    "fma.rn.f64 " S2 ", " A ", " A ", " S2 ";\n"
 #define RR_G8_STEP_HI(s, k, A, D0, D1, S2, S1)                                                           \
     "ld.shared.f64 " A ", [wq+" RR_G8_OFF_LO(k) "];\n"                                                   \
     "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {" D0 ", " D1 "}, {" A "}, {" RR_PB(s) "}, {" D0 ", " D1 "};\n" \
-    "fma.rn.f64 " S2 ", " A ", " A ", " S2 ";\n add.rn.f64 " S1 ", " S1 ", " A ";\n"
+    "fma.rn.f64 " S2 ", " A ", " A ", " S2 ";\n"
 // B fragment of the lanes that own pin j (predicate pq) from a tile column (wp / wq = fragment base of both halves)
 #define RR_G8_PB_LO(s) "@pq ld.shared.f64 " RR_PB(s) ", [wp+" RR_G8_OFF_LO(s) "];\n"
 #define RR_G8_PB_HI(s, k) "@pq ld.shared.f64 " RR_PB(s) ", [wq+" RR_G8_OFF_LO(k) "];\n"

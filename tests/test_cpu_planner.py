@@ -369,10 +369,11 @@ def test_deep_trees_spill_into_slots():
     assert abs(dots[plan.tab[0]] - want) <= 1e-12 * want
 
 
-def narrow_subset(batch, limit=None):
-    """candidates with at most 8 terms (what a G8 plan takes; the engine plans the wider ones the classic way)"""
+def narrow_subset(batch, limit=None, max_terms=7):
+    """candidates with at most 7 terms (what a G8 plan takes: a row meets its other terms, the centred target and the
+    column of ones as the eight pins; the engine plans the wider ones the classic way); R8 plans take 8"""
     m = np.diff(batch.cand_term_begin)
-    idx = [int(c) for c in np.nonzero(m <= 8)[0]]
+    idx = [int(c) for c in np.nonzero(m <= max_terms)[0]]
     return idx[:limit] if limit else idx
 
 
