@@ -2486,29 +2486,6 @@ struct R8Builder {
                     if (std::find(uni.begin(), uni.end(), s) == uni.end()) uni.push_back(s);
                 ++j;
             }
-            if (std::getenv("RR_B200_R8_DEBUG")) {
-                for (size_t r = i; r < j; ++r) {
-                    const Term &T = bp.term(pool[r].term);
-                    std::vector<std::string> st;
-                    static const char *nm[] = {"?", "c", "x", "+", "-", "*", "/", "sin", "cos", "ln", "exp", "sqrt", "sqr", "pow", "<", ">", "==", "!=", "min", "max"};
-                    for (size_t x = 0; x < T.nodes.size(); ++x) {
-                        const TermNode &nd = T.nodes[x];
-                        char buf[64];
-                        const bool stored_here = !nd.leaf() && is_stored(node_sid[pool[r].term][x]);
-                        std::string v;
-                        if (nd.op == RR_OP_CONST) { std::snprintf(buf, sizeof(buf), "%.4g", nd.cval); v = buf; }
-                        else if (nd.op == RR_OP_VAR) { std::snprintf(buf, sizeof(buf), "x%d", nd.var); v = buf; }
-                        else if (nd.right < 0) { v = std::string(nm[nd.op]) + "(" + st.back() + ")"; st.pop_back(); }
-                        else { std::string rr_ = st.back(); st.pop_back(); std::string ll = st.back(); st.pop_back(); v = "(" + ll + nm[nd.op] + rr_ + ")"; }
-                        if (stored_here) { std::snprintf(buf, sizeof(buf), "[S%d:", node_sid[pool[r].term][x]); v = std::string(buf) + v + "]"; }
-                        st.push_back(v);
-                    }
-                    std::fprintf(stderr, "   row %s\n", st.back().c_str());
-                }
-                std::fprintf(stderr, "group n=%d primary=%d shape=%016llx stored=%zu ops=%zu why=%s\n", (int)(j - i), pool[i].primary,
-                             (unsigned long long)pool[i].shape, uni.size(), term_prog[pool[i].term].ops.size(),
-                             j >= pool.size() ? "end" : (j - i >= 8 ? "full" : (pool[j].shape != pool[i].shape ? "shape" : "slots")));
-            }
             emit_group(&pool[i], (int)(j - i));
             i = j;
         }
@@ -2560,8 +2537,6 @@ struct R8Builder {
                 }
         }
         if (j < 0) { err = "internal: no pin available for a reduction partner"; return 0; }
-        if (std::getenv("RR_B200_R8_DEBUG"))
-            std::fprintf(stderr, "pin %d <- term %d (was %d), pool %zu\n", j, v, pin_term[j], pool.size());
         flush_pool();
         if (!err.empty()) return 0;
         const Term &T = bp.term(v);
