@@ -2546,8 +2546,21 @@ struct R8Builder {
         if (root.op == RR_OP_VAR) {
             col = col_of(root.var);
         } else if (root.op == RR_OP_CONST) {
-            err = "r8: constant term as a reduction partner";
-            return 0;
+            // a bare constant as a partner: through a temporary slot
+            const int32_t sl = alloc_slot();
+            if (!err.empty()) return 0;
+            RRIns l, st;
+            std::memset(&l, 0, sizeof(l));
+            std::memset(&st, 0, sizeof(st));
+            l.w0 = RQ_W0(RQ_LD, RQ_K);
+            l.imm = root.cval;
+            push(l);
+            st.w0 = RQ_W0(RQ_ST, RQ_M);
+            uint8_t c8[8];
+            for (int g = 0; g < 8; ++g) c8[g] = (uint8_t)(n_staged + sl);
+            std::memcpy(&st.imm, c8, 8);
+            push(st);
+            col = (uint32_t)(n_staged + sl);  // the slot stays free: nothing is emitted between here and the RQ_PINB
         } else {
             locked = node_sid[v][T.nodes.size() - 1];
             ensure_locked(locked);

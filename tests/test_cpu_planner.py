@@ -525,3 +525,96 @@ def test_terms_constant_by_construction_are_recognised():
     assert L.rr_debug_const_terms(C.byref(bs), 3, out) == 0
     for c, (_, want) in enumerate(cases):
         assert out[c] == (2 if want else 0), (c, out[c], want)
+
+
+def _design_numpy(Xfm, batch, c):
+    """The design matrix of candidate c evaluated with numpy's own functions, operation by operation in tree order -
+    the emulators' arithmetic (numpy's transcendentals differ from libm's by an ulp, which sin(exp(...)) of a random
+    tree turns into percents)."""
+    n = Xfm.shape[1]
+    cols = []
+    with np.errstate(all="ignore"):
+        for t in range(int(batch.cand_term_begin[c]), int(batch.cand_term_begin[c + 1])):
+            st = []
+            for w in batch.code[batch.term_code_begin[t]:batch.term_code_begin[t + 1]].tolist():
+                op, arg = w & 0xFF, w >> 8
+                if op == B.OP_CONST: st.append(np.full(n, float(batch.consts[arg])))
+                elif op == B.OP_VAR: st.append(Xfm[arg].copy())
+                elif B.ARITY[op] == 1:
+                    a = st.pop()
+                    st.append({B.OP_SIN: np.sin, B.OP_COS: np.cos, B.OP_LN: np.log, B.OP_EXP: np.exp, B.OP_SQRT: np.sqrt,
+                               B.OP_SQR: lambda v: v * v}[op](a))
+                else:
+                    r = st.pop()
+                    l = st.pop()
+                    if op == B.OP_PLUS: v = l + r
+                    elif op == B.OP_MINUS: v = l - r
+                    elif op == B.OP_MULTIPLY: v = l * r
+                    elif op == B.OP_DIVIDE: v = l / r
+                    elif op == B.OP_POW: v = np.power(l, r)
+                    elif op == B.OP_LESS_THAN: v = (l < r).astype(float)
+                    elif op == B.OP_GREATER_THAN: v = (l > r).astype(float)
+                    elif op == B.OP_EQUAL: v = (l == r).astype(float)
+                    elif op == B.OP_NOT_EQUAL: v = (l != r).astype(float)
+                    elif op == B.OP_MIN: v = np.where(l < r, l, r)
+                    else: v = np.where(l > r, l, r)
+                    st.append(v)
+            cols.append(st[-1])
+    cols.append(np.ones(n))
+    return np.stack(cols, axis=1)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["r8", "g8"])
+def test_row_and_g8_plans_on_random_neighbourhoods(seed, kind):
+    """Fuzz of the two large-n Gram planners: neighbourhoods of random candidates over all 19 opcodes that share base
+    terms (pins, stored sub-expressions, the second register, forced stores, segments, per-row constants, rare
+    operators, constant terms all come into play). Every reduction the solver reads must be the design-matrix product."""
+    rng = np.random.default_rng(100 + seed)
+    d, n = 5, 200
+    X = rng.uniform(0.2, 2.5, (n, d))
+    y = rng.normal(size=n)
+    base = [_random_expr(rng, d, 3) for _ in range(5)]
+    cands = []
+    for _ in range(150):
+        terms = list(base)
+        j = int(rng.integers(len(terms)))
+        r = rng.random()
+        if r < 0.35:
+            terms[j] = _random_expr(rng, d, 5)  # deep trees: two registers, forced stores
+        elif r < 0.65:
+            v = B.Expr.var(int(rng.integers(d)))
+            terms[j] = terms[j] * v if rng.random() < 0.5 else (terms[j] / v if rng.random() < 0.5 else v / terms[j])
+        elif r < 0.8:
+            terms[j] = B.Expr.const(float(np.round(rng.uniform(-2, 2), 2))) / terms[j]  # per-row constants
+        elif r < 0.9:
+            terms[j] = terms[j] / terms[j] if rng.random() < 0.5 else B.sin(B.Expr.const(float(np.round(rng.uniform(0.5, 3), 2))))
+        else:
+            terms.append(_random_expr(rng, d, 2))
+        cands.append(terms)
+    batch = B.Batch.from_exprs(B.MODE_OLS_FIT, cands)
+    cols = EMU.engine_columns(X, y)
+    if kind == "r8":
+        plan = EMU.Plan(batch, d, EMU.KIND_GRAM_R8, tile_cols=d + 32)
+        with np.errstate(all="ignore"):
+            dots, st = EMU.run_r8(plan, cols)
+        assert st["rows"] >= st["groups"] >= 1
+    else:
+        plan = EMU.Plan(batch, d, EMU.KIND_GRAM_G8, tile_cols=d + 7)
+        with np.errstate(all="ignore"):
+            dots, _ = EMU.run(plan, cols)
+    Xfm = O.feature_major(X)
+    yc = y - y.mean()
+    with np.errstate(all="ignore"):
+        for c in range(batch.n_cand):
+            A = _design_numpy(Xfm, batch, c)
+            G, byc = gram_from_dots(plan, dots, batch, c, n)
+            want = A.T @ A
+            scale = np.sqrt(np.abs(np.outer(np.diag(want), np.diag(want))))
+            ok = np.isclose(G, want, rtol=1e-11, atol=0, equal_nan=True) | (np.abs(G - want) <= 1e-12 * scale) | \
+                (~np.isfinite(want) & ~np.isfinite(G))
+            assert ok.all(), f"cand {c}"
+            wb = A[:, :-1].T @ yc
+            okb = np.isclose(byc, wb, rtol=1e-9, atol=1e-11 * np.sqrt(np.abs(np.diag(want)[:-1]) * float(yc @ yc)), equal_nan=True) | \
+                (~np.isfinite(wb) & ~np.isfinite(byc))
+            assert okb.all(), f"cand {c}"
